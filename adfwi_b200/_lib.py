@@ -1,0 +1,107 @@
+"""ctypes binding of the C ABI declared in include/adfwi_b200.h.
+
+``load()`` returns the product library ``csrc/libadfwi_b200.so`` and raises loudly when it is
+missing: there is no CPU / PyTorch fallback anywhere in this package.  ``bind()`` attaches the
+prototypes to any CDLL exporting the same ABI (the tests use it for the host-emulation build of
+the same sources).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libadfwi_b200.so")
+ABI_VERSION = 1
+
+c_f32p = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
+c_i64p = C.c_void_p
+
+
+class AcousticDesc(C.Structure):
+    """adfwi_acoustic_desc (include/adfwi_b200.h)."""
+    _fields_ = [
+        ("nzp", C.c_int32), ("nxp", C.c_int32),
+        ("ns", C.c_int32), ("nt", C.c_int32), ("nr", C.c_int32),
+        ("nabc", C.c_int32), ("free_surface", C.c_int32),
+        ("dt", C.c_float), ("c1", C.c_float), ("c2", C.c_float),
+        ("n_segments", C.c_int32), ("save_history", C.c_int32), ("ckpt_interval", C.c_int32),
+        ("need_g_alpha2", C.c_int32), ("shots_per_group", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+class ElasticDesc(C.Structure):
+    """adfwi_elastic_desc (include/adfwi_b200.h)."""
+    _fields_ = [
+        ("nzp", C.c_int32), ("nxp", C.c_int32),
+        ("ns", C.c_int32), ("nt", C.c_int32), ("nr", C.c_int32),
+        ("nz", C.c_int32), ("nx", C.c_int32), ("nabc", C.c_int32),
+        ("free_surface", C.c_int32), ("fd_order", C.c_int32), ("abc_pml", C.c_int32),
+        ("dt", C.c_float), ("dx", C.c_float), ("dz", C.c_float),
+        ("dt_dx", C.c_float), ("dt_dz", C.c_float), ("half_dt", C.c_float),
+        ("fdc", C.c_float * 3),
+        ("n_segments", C.c_int32), ("save_history", C.c_int32), ("ckpt_interval", C.c_int32),
+        ("shots_per_group", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+PtrArray5 = C.c_void_p * 5
+PtrArray6 = C.c_void_p * 6
+
+# every symbol include/adfwi_b200.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "adfwi_acoustic_workspace_bytes", "adfwi_acoustic_forward", "adfwi_acoustic_backward",
+    "adfwi_elastic_workspace_bytes", "adfwi_elastic_forward", "adfwi_elastic_backward",
+    "adfwi_strerror", "adfwi_abi_version", "adfwi_launch_count",
+]
+
+
+def bind(lib):
+    vp = C.c_void_p
+    lib.adfwi_acoustic_workspace_bytes.restype = C.c_size_t
+    lib.adfwi_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticDesc)]
+    lib.adfwi_acoustic_forward.restype = C.c_int
+    lib.adfwi_acoustic_forward.argtypes = [C.POINTER(AcousticDesc)] + [vp] * 5 + [vp] * 5 + [vp] * 3 + [vp] * 3 + [vp, C.c_size_t, vp]
+    lib.adfwi_acoustic_backward.restype = C.c_int
+    lib.adfwi_acoustic_backward.argtypes = [C.POINTER(AcousticDesc)] + [vp] * 5 + [vp] * 5 + [vp] * 3 + [vp] * 3 + [vp, C.c_size_t, vp]
+    if hasattr(lib, "adfwi_elastic_forward"):
+        lib.adfwi_elastic_workspace_bytes.restype = C.c_size_t
+        lib.adfwi_elastic_workspace_bytes.argtypes = [C.POINTER(ElasticDesc)]
+        lib.adfwi_elastic_forward.restype = C.c_int
+        lib.adfwi_elastic_forward.argtypes = [C.POINTER(ElasticDesc), C.POINTER(PtrArray6), vp, vp, vp, vp, vp, vp, vp, vp,
+                                              C.POINTER(PtrArray5), C.POINTER(PtrArray5), vp, C.c_size_t, vp]
+        lib.adfwi_elastic_backward.restype = C.c_int
+        lib.adfwi_elastic_backward.argtypes = [C.POINTER(ElasticDesc), C.POINTER(PtrArray6), vp, vp, vp, vp, vp, vp, vp, vp,
+                                               C.POINTER(PtrArray5), C.POINTER(PtrArray6), vp, vp, C.c_size_t, vp]
+    lib.adfwi_strerror.restype = C.c_char_p
+    lib.adfwi_strerror.argtypes = [C.c_int]
+    lib.adfwi_abi_version.restype = C.c_int
+    lib.adfwi_launch_count.restype = C.c_uint64
+    return lib
+
+
+_LIB = None
+
+
+def load():
+    """The product CUDA library.  Fails loudly (RuntimeError) if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"adfwi_b200: {LIB_PATH} is missing -- build it with `python -m adfwi_b200.build` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        lib = bind(C.CDLL(LIB_PATH))
+        if lib.adfwi_abi_version() != ABI_VERSION:
+            raise RuntimeError("adfwi_b200: libadfwi_b200.so ABI version mismatch; rebuild it")
+        _LIB = lib
+    return _LIB
+
+
+def check(lib, rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib.adfwi_strerror(rc).decode()} (code {rc})")
+
+
+def launch_count():
+    return int(load().adfwi_launch_count())

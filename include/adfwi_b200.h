@@ -1,0 +1,158 @@
+/*
+ * adfwi_b200.h -- C ABI of libadfwi_b200.so: sm_100a CUDA implementation of the wave-propagation
+ * hot path of liufeng2317/ADFWI (ADFWI/propagator/{acoustic,elastic}_kernels.py).
+ *
+ * The reference has no FFI of its own: its hot path is the pair of Python free functions
+ * `forward_kernel` (acoustic_kernels.py:179, elastic_kernels.py:917) whose body is the TorchScript
+ * time loop `step_forward*` plus the autograd tape PyTorch records through it.  Each entry point
+ * below replaces one such (implicit) unit; the citation says which.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - all arrays are dense row-major fp32 (indices int64), [z][x] with x fastest;
+ *   - the caller owns every buffer including the workspace; the library never allocates or
+ *     frees device memory and keeps no global state; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), no implicit synchronisation;
+ *   - return value: 0 = ok, <0 = ADFWI_E_* (argument error, detected before any launch),
+ *     >0 = cudaError_t of a failed launch.  adfwi_strerror() maps either to text.
+ */
+#ifndef ADFWI_B200_H
+#define ADFWI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADFWI_ABI_VERSION 1
+
+enum {
+    ADFWI_OK = 0,
+    ADFWI_E_NULL = -1,       /* required pointer is NULL */
+    ADFWI_E_DIMS = -2,       /* grid / counts out of the supported range */
+    ADFWI_E_WORKSPACE = -3,  /* workspace smaller than adfwi_*_workspace_bytes() */
+    ADFWI_E_ORDER = -4,      /* fd order not in {4,6} */
+    ADFWI_E_MODE = -5        /* backward called on a forward-only descriptor, etc. */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Iso-acoustic (p,u,w) solver.  Replaces acoustic_kernels.py:41-176 (step_forward, the time
+ * loop) and the autograd tape through it (acoustic_kernels.py:268-278 + loss.backward()).
+ * The coefficient planes are those of acoustic_kernels.py:257-265, computed by the caller.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nzp, nxp;        /* padded grid: nz+2*nabc, nx+2*nabc   (acoustic_kernels.py:230-231) */
+    int32_t ns, nt, nr;      /* shots in this call, time steps, receivers */
+    int32_t nabc;            /* absorbing-layer width; free_surface_start = nabc (FS) or 1 (:228) */
+    int32_t free_surface;    /* 0/1 */
+    float   dt;              /* f32(dt): source term is f32(dt)*src_v (:131) */
+    float   c1, c2;          /* f32(9/8), f32(-1/24) (:253-254) */
+    int32_t n_segments;      /* reference's checkpoint_segments: only shapes the literal
+                                semantics of forward_wavefield_u/w (:172-174, :286-288) */
+    int32_t save_history;    /* 0 = forward modelling only; 1 = keep what backward needs */
+    int32_t ckpt_interval;   /* K: state checkpoint every K steps, stencil history kept for K
+                                steps at a time (recomputed in backward).  K<=0 or K>=nt =
+                                store-all (no recomputation). */
+    int32_t need_g_alpha2;   /* 1 if d/d(alpha2) is wanted (density gradient) */
+    int32_t shots_per_group; /* shots advanced together (L2 residency); 0 = library picks */
+    int32_t reserved[4];
+} adfwi_acoustic_desc;
+
+/* bytes of workspace forward(+backward) needs for this descriptor (0 on invalid desc) */
+size_t adfwi_acoustic_workspace_bytes(const adfwi_acoustic_desc* desc);
+
+/*
+ * Forward sweep = acoustic_kernels.py:113-174 for nt steps from a zero state.
+ *   alpha1,alpha2,kappa1,kappa2,kappa3 : [nzp][nxp]
+ *   src_v [ns][nt]; src_x,src_z [ns]; rcv_x,rcv_z [nr]  -- PADDED grid indices (already +nabc)
+ *   rcv_p,rcv_u,rcv_w [ns][nt][nr]  (out; rcv_u / rcv_w may be NULL to skip)
+ *   illum_p,illum_u,illum_w [nzp-2nabc][nxp-2nabc] (out, each nullable):
+ *       the reference's forward_wavefield_{p,u,w} (literal semantics)
+ */
+int adfwi_acoustic_forward(const adfwi_acoustic_desc* desc,
+                           const float* alpha1, const float* alpha2, const float* kappa1,
+                           const float* kappa2, const float* kappa3,
+                           const float* src_v, const int64_t* src_x, const int64_t* src_z,
+                           const int64_t* rcv_x, const int64_t* rcv_z,
+                           float* rcv_p, float* rcv_u, float* rcv_w,
+                           float* illum_p, float* illum_u, float* illum_w,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Adjoint sweep = what autograd computes for the tape of the same loop: given the record
+ * cotangents g_rcv_* [ns][nt][nr] (each nullable = zero) accumulate
+ *   g_alpha1, g_alpha2 [nzp][nxp]  (OVERWRITTEN; summed over the ns shots; g_alpha2 nullable)
+ *   g_src_v [ns][nt]               (nullable)
+ * `workspace` must be the buffer the matching forward call (save_history=1) filled.
+ */
+int adfwi_acoustic_backward(const adfwi_acoustic_desc* desc,
+                            const float* alpha1, const float* alpha2, const float* kappa1,
+                            const float* kappa2, const float* kappa3,
+                            const float* src_v, const int64_t* src_x, const int64_t* src_z,
+                            const int64_t* rcv_x, const int64_t* rcv_z,
+                            const float* g_rcv_p, const float* g_rcv_u, const float* g_rcv_w,
+                            float* g_alpha1, float* g_alpha2, float* g_src_v,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2-D P-SV elastic solver (iso / VTI / HTI through Cij planes).  Replaces
+ * elastic_kernels.py:223-423 / :426-579 (step_forward_PML_{4,6}order),
+ * :586-777 / :781-912 (step_forward_ABL_{4,6}order) and the autograd tape through them.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nzp, nxp;        /* padded grid incl. the fs_offset rows (elastic_kernels.py:286-287) */
+    int32_t ns, nt, nr;
+    int32_t nz, nx, nabc;    /* physical grid + layer width (illumination crop, :414-418) */
+    int32_t free_surface;    /* 0/1 */
+    int32_t fd_order;        /* 4 or 6 (anything else is rejected; the Python shim maps !=4 -> 6) */
+    int32_t abc_pml;         /* 1 = split-field PML (:223), 0 = multiplicative sponge/ABL (:586) */
+    float   dt, dx, dz;      /* f32 roundings of the python floats */
+    float   dt_dx, dt_dz;    /* f32(dt/dx), f32(dt/dz) (division done in double, :325-326) */
+    float   half_dt;         /* f32(0.5*dt) (:313-316) */
+    float   fdc[3];          /* DiffCoef(NN,'s') bits (:20-58) */
+    int32_t n_segments;      /* n_segments: shapes the illumination maps (:1017-1021) */
+    int32_t save_history;
+    int32_t ckpt_interval;
+    int32_t shots_per_group;
+    int32_t reserved[4];
+} adfwi_elastic_desc;
+
+size_t adfwi_elastic_workspace_bytes(const adfwi_elastic_desc* desc);
+
+/*
+ * coef  : 6 planes [nzp][nxp] in the order C11,C13,C33,C55,bx,bz (C15 = C35 = 0 for every model
+ *         the reference can build, parameters.py:38-44; adding 0*x is exact, so they are dropped)
+ * bcx,bcz [nzp][nxp] (PML) or damp [nzp][nxp] in bcx with bcz=NULL (ABL)
+ * mt    : [ns][3][3] moment tensors;  src_v [ns][nt];  indices are PADDED grid indices
+ * rcv   : 5 record arrays [ns][nt][nr] in the order txx,tzz,txz,vx,vz (out)
+ * illum : 5 maps [nz][nx], same order (out, nullable as a whole)
+ */
+int adfwi_elastic_forward(const adfwi_elastic_desc* desc, const float* const* coef,
+                          const float* bcx, const float* bcz, const float* mt,
+                          const float* src_v, const int64_t* src_x, const int64_t* src_z,
+                          const int64_t* rcv_x, const int64_t* rcv_z,
+                          float* const* rcv, float* const* illum,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* g_rcv: 5 cotangent arrays (entries nullable); g_coef: 6 planes [nzp][nxp] (OVERWRITTEN);
+ * g_src_v nullable. */
+int adfwi_elastic_backward(const adfwi_elastic_desc* desc, const float* const* coef,
+                           const float* bcx, const float* bcz, const float* mt,
+                           const float* src_v, const int64_t* src_x, const int64_t* src_z,
+                           const int64_t* rcv_x, const int64_t* rcv_z,
+                           const float* const* g_rcv, float* const* g_coef, float* g_src_v,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* misc */
+const char* adfwi_strerror(int code);
+int adfwi_abi_version(void);
+/* number of kernels the library has launched in this process (bench.py's gpu_launches) */
+uint64_t adfwi_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADFWI_B200_H */
