@@ -50,9 +50,17 @@ PtrArray6 = C.c_void_p * 6
 
 # every symbol include/adfwi_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
-    "adfwi_acoustic_workspace_bytes", "adfwi_acoustic_forward", "adfwi_acoustic_backward",
+    "adfwi_acoustic_workspace_bytes", "adfwi_acoustic_group_size", "adfwi_acoustic_forward", "adfwi_acoustic_backward",
     "adfwi_elastic_workspace_bytes", "adfwi_elastic_forward", "adfwi_elastic_backward",
     "adfwi_strerror", "adfwi_abi_version", "adfwi_launch_count",
+    "adfwi_timing_enable", "adfwi_timing_collect",
+]
+
+# enum KernelClass of csrc/common.cuh
+KERNEL_CLASSES = [
+    "ac_fwd_p", "ac_fwd_uw", "ac_record", "ac_adj_inject", "ac_adj_a", "ac_adj_b",
+    "el_fwd_stress", "el_fwd_vel", "el_record", "el_adj_inject", "el_adj_vel", "el_adj_stress",
+    "ac_fwd_fused", "ac_adj_fused", "other",
 ]
 
 
@@ -60,6 +68,8 @@ def bind(lib):
     vp = C.c_void_p
     lib.adfwi_acoustic_workspace_bytes.restype = C.c_size_t
     lib.adfwi_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticDesc)]
+    lib.adfwi_acoustic_group_size.restype = C.c_int
+    lib.adfwi_acoustic_group_size.argtypes = [C.POINTER(AcousticDesc)]
     lib.adfwi_acoustic_forward.restype = C.c_int
     lib.adfwi_acoustic_forward.argtypes = [C.POINTER(AcousticDesc)] + [vp] * 5 + [vp] * 5 + [vp] * 3 + [vp] * 3 + [vp, C.c_size_t, vp]
     lib.adfwi_acoustic_backward.restype = C.c_int
@@ -77,6 +87,10 @@ def bind(lib):
     lib.adfwi_strerror.argtypes = [C.c_int]
     lib.adfwi_abi_version.restype = C.c_int
     lib.adfwi_launch_count.restype = C.c_uint64
+    lib.adfwi_timing_enable.restype = None
+    lib.adfwi_timing_enable.argtypes = [C.c_int]
+    lib.adfwi_timing_collect.restype = C.c_int
+    lib.adfwi_timing_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
     return lib
 
 
@@ -105,3 +119,15 @@ def check(lib, rc, what):
 
 def launch_count():
     return int(load().adfwi_launch_count())
+
+
+def timing_enable(every_n):
+    load().adfwi_timing_enable(int(every_n))
+
+
+def timing_collect():
+    """{kernel class: (summed ms of the sampled launches, samples)} and clear the samples."""
+    n = len(KERNEL_CLASSES)
+    ms = (C.c_float * n)(); cnt = (C.c_int * n)()
+    load().adfwi_timing_collect(ms, cnt, n)
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES) if cnt[i] > 0}

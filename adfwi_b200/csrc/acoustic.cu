@@ -404,12 +404,12 @@ static int ac_forward_step(const AcPlan& P, cudaStream_t st, int sb, int se, int
     const dim3 blk(64, 4);
     ShotRange sr{sb, se, P.spt};
     const dim3 grd = ac_grid(P, cdiv(se - sb, P.spt), blk);
-#define LP(FSv, SAVEv) ADFWI_LAUNCH(ADFWI_KERNEL(ac_fwd_p<FSv, SAVEv>), grd, blk, st, P.g, sr, a1, k1, P.p, P.u, P.w, src_v, sx, sz, P.histS, P.K, tl, it)
+#define LP(FSv, SAVEv) do { TimedLaunch tl_(KC_AC_FWD_P, st); ADFWI_LAUNCH(ADFWI_KERNEL(ac_fwd_p<FSv, SAVEv>), grd, blk, st, P.g, sr, a1, k1, P.p, P.u, P.w, src_v, sx, sz, P.histS, P.K, tl, it); } while (0)
     if (P.FS) { if (save) LP(true, true); else LP(true, false); }
     else      { if (save) LP(false, true); else LP(false, false); }
 #undef LP
     ADFWI_LAUNCH_CHECK();
-#define LU(FSv, ILv) ADFWI_LAUNCH(ADFWI_KERNEL(ac_fwd_uw<FSv, ILv>), grd, blk, st, P.g, sr, a2, k2, k3, P.p, P.u, P.w, P.ill_p, P.ill_u, acc_u)
+#define LU(FSv, ILv) do { TimedLaunch tl_(KC_AC_FWD_UW, st); ADFWI_LAUNCH(ADFWI_KERNEL(ac_fwd_uw<FSv, ILv>), grd, blk, st, P.g, sr, a2, k2, k3, P.p, P.u, P.w, P.ill_p, P.ill_u, acc_u); } while (0)
     if (P.FS) { if (illum) LU(true, true); else LU(true, false); }
     else      { if (illum) LU(false, true); else LU(false, false); }
 #undef LU
@@ -431,6 +431,13 @@ extern "C" size_t adfwi_acoustic_workspace_bytes(const adfwi_acoustic_desc* desc
     AcPlan P;
     if (ac_make_plan(desc, nullptr, &P) != ADFWI_OK) return 0;
     return P.bytes;
+}
+
+extern "C" int adfwi_acoustic_group_size(const adfwi_acoustic_desc* desc)
+{
+    AcPlan P;
+    if (ac_make_plan(desc, nullptr, &P) != ADFWI_OK) return 0;
+    return P.G;
 }
 
 extern "C" int adfwi_acoustic_forward(const adfwi_acoustic_desc* desc,
@@ -479,6 +486,7 @@ extern "C" int adfwi_acoustic_forward(const adfwi_acoustic_desc* desc,
                                  src_v, src_x, src_z, illum, it >= last_chunk_start);
             if (rc) return rc;
             if (P.nr > 0) {
+                TimedLaunch tl_(KC_AC_RECORD, st);
                 ADFWI_LAUNCH(ADFWI_KERNEL(ac_record), dim3(cdiv(P.nr, 128), se - sb), 128, st, g, sb, se, P.nr, P.p, P.u, P.w, rcv_x, rcv_z,
                                                                           rcv_p, rcv_u, rcv_w, it);
                 ADFWI_LAUNCH_CHECK();
@@ -554,19 +562,23 @@ extern "C" int adfwi_acoustic_backward(const adfwi_acoustic_desc* desc,
             for (int it = t1 - 1; it >= t0; --it) {
                 const int tl = it - t0;
                 if (have_g) {
+                    TimedLaunch tl_(KC_AC_ADJ_INJECT, st);
                     ADFWI_LAUNCH(ADFWI_KERNEL(ac_adj_inject), dim3(cdiv(P.nr, 128), se - sb), 128, st, g, sb, se, P.nr, P.lpY, P.lu, P.lw,
                                                                                   rcv_x, rcv_z, g_rcv_p, g_rcv_u, g_rcv_w, it);
                     ADFWI_LAUNCH_CHECK();
                 }
-#define LA(FSv, G2v) ADFWI_LAUNCH(ADFWI_KERNEL(ac_adj_a<FSv, G2v>), grd, blk, st, g, sr, alpha2, P.lpY, P.lu, P.lw, P.lpX, P.histP, P.K, tl, P.g2part)
+#define LA(FSv, G2v) do { TimedLaunch tl_(KC_AC_ADJ_A, st); ADFWI_LAUNCH(ADFWI_KERNEL(ac_adj_a<FSv, G2v>), grd, blk, st, g, sr, alpha2, P.lpY, P.lu, P.lw, P.lpX, P.histP, P.K, tl, P.g2part); } while (0)
                 if (P.FS) { if (P.need_g2) LA(true, true); else LA(true, false); }
                 else      { if (P.need_g2) LA(false, true); else LA(false, false); }
 #undef LA
                 ADFWI_LAUNCH_CHECK();
+                {
+                TimedLaunch tl_(KC_AC_ADJ_B, st);
                 if (P.FS) ADFWI_LAUNCH(ADFWI_KERNEL(ac_adj_b<true>), grd, blk, st, g, sr, alpha1, kappa1, kappa2, kappa3, P.lpX, P.lpY, P.lu, P.lw,
                                                               P.histS, P.K, tl, P.g1part, src_x, src_z, g_src_v, it);
                 else      ADFWI_LAUNCH(ADFWI_KERNEL(ac_adj_b<false>), grd, blk, st, g, sr, alpha1, kappa1, kappa2, kappa3, P.lpX, P.lpY, P.lu, P.lw,
                                                                P.histS, P.K, tl, P.g1part, src_x, src_z, g_src_v, it);
+                }
                 ADFWI_LAUNCH_CHECK();
             }
         }

@@ -34,6 +34,24 @@ struct Carver {
     }
 };
 
+// ---- optional sampled per-kernel-class device timing (diagnostics for bench.py's roofline) ----
+// When enabled through adfwi_timing_enable(every_n), every n-th launch of each class is bracketed
+// by CUDA events recorded on the launching stream; adfwi_timing_collect() reads them back.
+enum KernelClass {
+    KC_AC_FWD_P = 0, KC_AC_FWD_UW, KC_AC_RECORD, KC_AC_ADJ_INJECT, KC_AC_ADJ_A, KC_AC_ADJ_B,
+    KC_EL_FWD_STRESS, KC_EL_FWD_VEL, KC_EL_RECORD, KC_EL_ADJ_INJECT, KC_EL_ADJ_VEL, KC_EL_ADJ_STRESS,
+    KC_AC_FWD_FUSED, KC_AC_ADJ_FUSED, KC_OTHER, KC_COUNT
+};
+#ifdef ADFWI_HOST_EMUL
+struct TimedLaunch { TimedLaunch(int, cudaStream_t) {} };
+#else
+struct TimedLaunch {      // RAII: start event in the constructor, stop event in the destructor
+    int slot; cudaStream_t st;
+    TimedLaunch(int cls, cudaStream_t s);
+    ~TimedLaunch();
+};
+#endif
+
 #define ADFWI_LAUNCH_CHECK()                                   \
     do {                                                       \
         ::adfwi::g_launches.fetch_add(1, std::memory_order_relaxed); \

@@ -1,1 +1,3 @@
-from . import acoustic_kernels  # noqa: F401
+from . import acoustic_kernels, boundary_condition  # noqa: F401
+from .acoustic_propagator import AcousticPropagator  # noqa: F401
+from .boundary_condition import bc_gerjan, bc_pml, bc_pml_xz, bc_sincos  # noqa: F401

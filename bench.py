@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- FWI-gradient throughput of the wave-propagation hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU, NCCL; launched by the driver)
+
+A "step" = one FWI gradient over this rank's shots: for every shot batch forward modelling,
+L2 waveform misfit against observed records, adjoint sweep, gradient accumulation; then (N>1) one
+all-reduce of the model gradient.  Workload (default C2, BASELINE.json configs[1]): iso-acoustic
+350x1700 grid (10 m, 50-cell PML + free surface -> 450x1800 padded), nt=4000, 1700 receivers,
+240 shots over 8 GPUs = 30 shots per GPU (weak scaling: per-GPU work fixed).  Synthetic model,
+random-free analytic velocity; observed data = our own forward modelling of the
+"true" model, generated before the timed region.
+
+metric `value`: 2*nzp*nxp*nt*shots / time  (forward + adjoint cell-updates per second, summed over
+GPUs), inputs resident in HBM.  `e2e`: same through AcousticPropagator.forward()+backward() with
+the model, wavelets and observed data starting in pinned HOST memory and gradient+loss read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nz, nx, dx, dt, nt, f0, nabc, shots_total_at_8gpus, nr, batch_size)
+    "C1": dict(nz=88, nx=200, dx=40.0, dt=3e-3, nt=1600, f0=5.0, nabc=30, shots8=40 * 8, nr=200, batch=40,
+               desc="iso-acoustic Marmousi2 example 88x200 (148x260 padded), nt=1600"),
+    "C2": dict(nz=350, nx=1700, dx=10.0, dt=1e-3, nt=4000, f0=10.0, nabc=50, shots8=240, nr=1700, batch=10,
+               desc="iso-acoustic Marmousi2 full-res 350x1700 (450x1800 padded), nt=4000, 240 shots / 8 GPUs"),
+    "C5": dict(nz=2048, nx=8192, dx=5.0, dt=5e-4, nt=1000, f0=15.0, nabc=50, shots8=8 * 2, nr=8192, batch=2,
+               desc="synthetic acoustic 2048x8192 (2148x8292 padded), 1000-step slice of nt=8000, 2 shots/GPU"),
+}
+# algorithmic bytes per cell-update
+B_FWD_SAVE = 36.0     # forward sweep in recording mode: p,u,w r+w 24 + alpha1,alpha2 8 + S write 4
+B_ADJ = 44.0          # adjoint sweep (vp only): 3 adjoint fields r+w 24 + alpha1,alpha2 8 + S read 4 + g_alpha1 RMW 8
+B_GRAD_STEP = 80.0    # forward(recording) + adjoint per cell-step = 40 B per cell-update
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax = max(smax, float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle (port of the reference time loop + its adjoint)
+# ------------------------------------------------------------------------------------------------
+def cpu_gradient_sample(wl, ns, nt):
+    """Time forward+adjoint of the oracle on a bounded sample (ns shots x nt steps) of the
+    workload's grid with all host threads.  Returns (cell_updates_per_s, seconds)."""
+    from oracle import oracle as O
+    from adfwi_b200 import synthetic as syn
+    from adfwi_b200.propagator.boundary_condition import bc_pml
+    nz, nx, nabc = wl["nz"], wl["nx"], wl["nabc"]
+    vp = syn.smooth2d(syn.marmousi_like_vp(nz, nx), 6)
+    rho = syn.gardner_rho(vp)
+    damp = bc_pml(nx, nz, wl["dx"], wl["dx"], pml=nabc, vmax=float(vp.max()), free_surface=False).astype(np.float32)
+    coef = O.acoustic_coefficients(vp, rho, damp, wl["dt"], wl["dx"], nabc, True)
+    sx = np.round(np.linspace(2, nx - 3, ns)).astype(np.int64); sz = np.ones(ns, np.int64)
+    rx = np.round(np.linspace(0, nx - 1, wl["nr"])).astype(np.int64); rz = np.ones(wl["nr"], np.int64)
+    wav = np.broadcast_to(syn.integrated_ricker(nt, wl["dt"], wl["f0"] * 4).astype(np.float32), (ns, nt)).copy()
+    O.lib()
+    t0 = time.perf_counter()
+    # one forward sweep (with history), residual-like cotangent from the records, one adjoint sweep
+    O.acoustic_run(coef, nabc, True, wl["dt"], sx, sz, wav, rx, rz, g_rcv=lambda rec: (rec["p"], None, None),
+                   need_g_alpha2=False)
+    sec = time.perf_counter() - t0
+    cells = (nz + 2 * nabc) * (nx + 2 * nabc) * ns * nt
+    return 2.0 * cells / sec, sec
+
+
+def cpu_sample_size():
+    """Bounded CPU sample: the oracle's adjoint parallelises over shots, so give it one shot per
+    host thread (up to 16) for 50 time steps."""
+    return max(2, min(os.cpu_count() or 2, 16)), 50
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ns, nt = cpu_sample_size()
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        v, s = cpu_gradient_sample(wl, ns, nt)
+        if i >= args.warmup:
+            vals.append(v); secs.append(s)
+    val = float(np.mean(vals)) / 1e9
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": val,
+        "unit": "Gcell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "sample": f"{ns} shots x {nt} steps of the same padded grid"},
+        "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle/ C port of the reference time loop + adjoint, OpenMP over {cores} host threads, "
+                                   f"{ns} shots x {nt} steps of the {args.workload} grid per step"},
+        "e2e": {"value": val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    from adfwi_b200 import _lib, distributed as D, fwi, synthetic as syn
+    from adfwi_b200.propagator import AcousticPropagator
+
+    rank, local, world = D.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+
+    nz, nx, nabc, nt, dt, dx = wl["nz"], wl["nx"], wl["nabc"], wl["nt"], wl["dt"], wl["dx"]
+    ns_local = max(wl["shots8"] // 8, 1)
+    ns_total = ns_local * world
+    lo, hi = D.shard_shots(ns_total, rank, world)
+    batch = min(wl["batch"], ns_local)
+    nzp, nxp = nz + 2 * nabc, nx + 2 * nabc
+
+    vp_true = syn.marmousi_like_vp(nz, nx)
+    vp_init = syn.smooth2d(vp_true, 6)
+    survey = syn.surface_survey(nx, ns_total, wl["nr"], nt, dt, wl["f0"])
+    true_model = syn.AcousticGridModel(vp_true, dx=dx, dz=dx, nabc=nabc, free_surface=True, vp_grad=False, device=dev)
+    model = syn.AcousticGridModel(vp_init, dx=dx, dz=dx, nabc=nabc, free_surface=True, vp_grad=True, device=dev)
+    prop_true = AcousticPropagator(true_model, survey, device=dev)
+    prop = AcousticPropagator(model, survey, device=dev)
+    prop.damp = prop_true.damp            # same absorbing profile for both (vmax of the true model)
+    shots = np.arange(lo, hi)
+
+    # observed data of this rank's shots (untimed set-up), device copy + pinned host copy
+    obs = torch.empty((len(shots), nt, wl["nr"]), device=dev)
+    with torch.no_grad():
+        for pos in fwi.shot_batches(len(shots), batch):
+            obs[pos] = prop_true.forward(shot_index=shots[pos])["p"]
+    obs_host = obs.cpu().pin_memory()
+    vp_host = model.vp.detach().cpu().pin_memory()
+    wav_host = prop.wavelet.detach().cpu().pin_memory()
+    grad_host = torch.empty((nz, nx), dtype=torch.float32).pin_memory()
+    del prop_true, true_model
+    torch.cuda.empty_cache()
+
+    def step_resident():
+        model.vp.grad = None
+        loss, illum = fwi.acoustic_gradient(prop, obs, shots=shots, batch_size=batch)
+        D.allreduce_gradients([model.vp], extras=[illum, loss])
+        return loss
+
+    def step_e2e():
+        # inputs start in pinned host memory: model, wavelets, observed records of every batch
+        model.vp.grad = None
+        with torch.no_grad():
+            model.vp.copy_(vp_host, non_blocking=True)
+            prop.wavelet.copy_(wav_host, non_blocking=True)
+        loader = lambda pos: obs_host[pos[0]:pos[-1] + 1].to(dev, non_blocking=True)
+        loss, illum = fwi.acoustic_gradient(prop, None, shots=shots, batch_size=batch, obs_loader=loader)
+        D.allreduce_gradients([model.vp], extras=[illum, loss])
+        grad_host.copy_(model.vp.grad, non_blocking=True)
+        return float(loss.item())      # device->host read of the loss (synchronises)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start(); time.sleep(0.3)
+    n0 = _lib.launch_count()
+    _lib.timing_collect()
+    _lib.timing_enable(max(16 * args.steps, 16))
+    t_wall0 = time.time()
+    ms = timed(step_resident, args.steps)
+    t_wall1 = time.time()
+    _lib.timing_enable(0)
+    launches = _lib.launch_count() - n0
+    kt = _lib.timing_collect()
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    updates_per_step = 2.0 * nzp * nxp * nt * ns_total
+    value = updates_per_step * args.steps / (ms * 1e-3) / 1e9
+    e2e_value = updates_per_step * args.steps / (ms_e2e * 1e-3) / 1e9
+    lt = torch.tensor([float(launches)], device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    h2d = vp_host.numel() * 4 + wav_host.numel() * 4 + obs_host.numel() * 4
+    d2h = grad_host.numel() * 4 + 4
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        # dominant kernel (pair): sampled average launch durations from CUDA events on the launch stream
+        avg = {k: v[0] / v[1] for k, v in kt.items()}
+        G_cells = None
+        roof = None
+        if avg:
+            adj = sum(avg.get(k, 0.0) for k in ("ac_adj_a", "ac_adj_b", "ac_adj_inject", "ac_adj_fused"))
+            fwd = sum(avg.get(k, 0.0) for k in ("ac_fwd_p", "ac_fwd_uw", "ac_record", "ac_fwd_fused"))
+            # cells one launch processes: shots of one library shot group x padded plane
+            import ctypes
+            from adfwi_b200.propagator.acoustic_kernels import config as ak_config, make_desc
+            d = make_desc(nzp, nxp, batch, nt, wl["nr"], nabc, True, dt, 1, True, 0, False, ak_config["shots_per_group"])
+            G = lib.adfwi_acoustic_group_size(ctypes.byref(d))   # shots one launch advances
+            G_cells = G * nzp * nxp
+            dom_name, dom_ms, dom_bytes = ("adjoint step (ac_adj_inject+ac_adj_a+ac_adj_b)", adj, B_ADJ) if adj >= fwd else \
+                                          ("forward step (ac_fwd_p+ac_fwd_uw+ac_record)", fwd, B_FWD_SAVE)
+            if dom_ms > 0:
+                ach = dom_bytes * G_cells / (dom_ms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "kernel": dom_name, "avg_launch_ms": dom_ms,
+                        "algorithmic_bytes_per_cell_update": dom_bytes, "cells_per_launch": G_cells,
+                        "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                        "whole_step_frac": B_GRAD_STEP / 2 * value * 1e9 / world / (peak * 1e9),
+                        "per_kernel_avg_ms": avg}
+        cns, cnt = cpu_sample_size()
+        cpu_v, cpu_s = cpu_gradient_sample(wl, cns, cnt)
+        line = {
+            "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": value, "unit": "Gcell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "shots_per_gpu": ns_local, "shots_total": ns_total,
+                       "batch_size": batch, "padded_grid": [nzp, nxp], "nt": nt, "receivers": wl["nr"],
+                       "l2": "working set per step >> 126 MB L2 (inputs larger than L2; no explicit flush)",
+                       "parallelism": f"shots sharded over {world} GPU(s), one all-reduce of the gradient"},
+            "shots_per_s": ns_total * args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(lt.item()),
+            "roofline": roof,
+            "cpu_baseline": {"value": cpu_v / 1e9, "unit": "Gcell-updates/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"oracle/ C port (OpenMP, all host threads), {cns} shots x {cnt} steps of the {args.workload} grid, "
+                                       f"forward+adjoint, {cpu_s:.1f} s"},
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,8 @@ typedef struct {
 
 /* bytes of workspace forward(+backward) needs for this descriptor (0 on invalid desc) */
 size_t adfwi_acoustic_workspace_bytes(const adfwi_acoustic_desc* desc);
+/* shots one kernel launch advances for this descriptor (the library's L2-residency grouping) */
+int adfwi_acoustic_group_size(const adfwi_acoustic_desc* desc);
 
 /*
  * Forward sweep = acoustic_kernels.py:113-174 for nt steps from a zero state.
@@ -151,6 +153,15 @@ const char* adfwi_strerror(int code);
 int adfwi_abi_version(void);
 /* number of kernels the library has launched in this process (bench.py's gpu_launches) */
 uint64_t adfwi_launch_count(void);
+
+
+/* Diagnostics for the bench roofline: when every_n > 0, every n-th launch of each kernel class is
+ * bracketed by CUDA events on its stream (process-wide switch, off by default, every_n = 0 turns
+ * it off).  adfwi_timing_collect() synchronises the recorded events, writes per-class summed
+ * milliseconds and sample counts (arrays of length n), clears the samples and returns the number
+ * of kernel classes.  Class ids: see enum KernelClass in csrc/common.cuh / adfwi_b200/_lib.py. */
+void adfwi_timing_enable(int every_n);
+int adfwi_timing_collect(float* ms_sum_host, int* count_host, int n);
 
 #ifdef __cplusplus
 }
