@@ -100,3 +100,52 @@ def surface_survey(nx, ns, nr, nt, dt, f0, src_z=1, rcv_z=1):
     src = Source(np.stack([sx, np.full(ns, src_z)], 1), integrated_ricker(nt, dt, f0), nt, dt, f0)
     rcv = Receiver(np.stack([rx, np.full(nr, rcv_z)], 1))
     return Survey(src, rcv)
+
+
+class ElasticGridModel(torch.nn.Module):
+    """vp, vs, rho (+ Thomsen eps, delta, gamma) on an (nz,nx) grid exposing what ElasticPropagator
+    reads after ``forward()``: ``lamu, lam, bx, bz, CC`` (21 moduli; C11,C13,C33,C55 used).
+
+    The parameterisation restates the physics of ADFWI/model/parameters.py in plain torch so that
+    autograd carries the propagator's coefficient-plane gradients back to the model parameters:
+    C33 = vp^2 rho, C44 = vs^2 rho, C11 = C33 (1+2 eps), C66 = C44 (1+2 gamma),
+    C13 = sqrt(2 C33 (C33-C44) delta + (C33-C44)^2) - C44 (:102-107), C55 = C44 (VTI / isotropic),
+    b = 1/rho, bx/bz = two-point averages of b, C55 <- 0.2*(five-point average counting the lower
+    neighbour twice) (:199-212).  Isotropic models are the eps = delta = gamma = 0 case."""
+
+    def __init__(self, vp, vs, rho, eps=None, delta=None, gamma=None, dx=10.0, dz=10.0, ox=0.0, oz=0.0,
+                 nabc=50, free_surface=True, abc_type="PML", requires_grad=("vp", "vs", "rho"), device="cuda"):
+        super().__init__()
+        t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(device)
+        vp = t(vp)
+        self.nz, self.nx = vp.shape
+        self.dx, self.dz, self.ox, self.oz = dx, dz, ox, oz
+        self.nabc, self.free_surface, self.abc_type = nabc, free_surface, abc_type
+        self.abc_jerjan_alpha = 0.0053
+        zeros = torch.zeros_like(vp)
+        vals = dict(vp=vp, vs=t(vs), rho=t(rho), eps=zeros.clone() if eps is None else t(eps),
+                    delta=zeros.clone() if delta is None else t(delta), gamma=zeros.clone() if gamma is None else t(gamma))
+        for k, v in vals.items():
+            setattr(self, k, torch.nn.Parameter(v, requires_grad=k in requires_grad))
+        self.lamu = self.lam = self.bx = self.bz = self.CC = None
+
+    def forward(self):
+        vp, vs, rho = self.vp, self.vs, self.rho
+        C33 = vp ** 2 * rho
+        C44 = vs ** 2 * rho
+        C11 = C33 * (1 + 2 * self.eps)
+        C66 = C44 * (1 + 2 * self.gamma)
+        C13 = torch.sqrt(2 * C33 * (C33 - C44) * self.delta + (C33 - C44) ** 2) - C44
+        self.lamu, self.lam = C33, C33 - 2 * C44
+        b = 1 / rho
+        nz, nx = self.nz, self.nx
+        self.bx = 0.5 * (b[:, 0:nx - 1] + b[:, 1:nx])
+        self.bz = 0.5 * (b[0:nz - 1, :] + b[1:nz, :])
+        C55 = C44
+        C55s = 0.2 * (C55[1:nz - 1, 1:nx - 1] + C55[2:nz, 1:nx - 1] + C55[1:nz - 1, 2:nx] + C55[2:nz, 1:nx - 1] + C55[2:nz, 2:nx])
+        zero = torch.zeros_like(vp)
+        CC = [zero] * 21
+        CC[0], CC[2], CC[11], CC[18] = C11, C13, C33, C55s
+        CC[15], CC[20] = C44, C66
+        self.CC = CC
+        return None

@@ -1,0 +1,88 @@
+"""GPU parity of the elastic path (through the C ABI via the drop-in forward_kernel) against the
+committed golden fixtures of the unmodified reference: all eight variants
+{split-PML, Cerjan sponge} x {O(2,4), O(2,6)} x {free surface on, off}."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REC_TOL = 1e-5     # BASELINE.json: synthetic shot records rel-L2 <= 1e-5
+GRAD_TOL = 1e-4    # BASELINE.json: gradients rel-L2 <= 1e-4
+COMPS = ("txx", "tzz", "txz", "vx", "vz")
+PLANES = ("C11", "C13", "C33", "C55", "bx", "bz")
+CASES = [f"elastic_{abc}_o{o}_{fs}" for abc in ("pml", "gerjan") for o in (4, 6) for fs in ("fs", "nofs")]
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _run(g, use, **cfg):
+    from adfwi_b200.propagator import acoustic_kernels as ak, elastic_kernels as ek
+    old = dict(ak.config)
+    ak.config.update(cfg)
+    try:
+        dev = torch.device("cuda:0")
+        t = lambda k: torch.tensor(g[k], device=dev)
+        nz, nx = int(g["nz"]), int(g["nx"])
+        leaves = {k: t("in_" + k).requires_grad_(True) for k in PLANES}
+        zero = torch.zeros((nz, nx), device=dev)
+        CC = [zero] * 21
+        CC[0], CC[2], CC[11], CC[18] = leaves["C11"], leaves["C13"], leaves["C33"], leaves["C55"]
+        abc = str(g["abc"])
+        bcx = t("bcx") if abc == "PML" else None
+        bcz = t("bcz") if abc == "PML" else None
+        damp = None if abc == "PML" else t("damp")
+        rec = ek.forward_kernel(nx, nz, float(g["dx"]), float(g["dz"]), int(g["nt"]), float(g["dt"]), int(g["nabc"]),
+                                bool(g["free_surface"]), t("src_x"), t("src_z"), len(g["src_x"]), t("src_v"), t("mt"),
+                                t("rcv_x"), t("rcv_z"), len(g["rcv_x"]), abc, bcx, bcz, damp, None, None,
+                                leaves["bx"], leaves["bz"], CC, fd_order=int(g["order"]), n_segments=int(g["segments"]),
+                                device=dev, dtype=torch.float32)
+        sum((rec[k] * t("W_" + k)).sum() for k in use).backward()
+        return rec, {k: v.grad.cpu().numpy() for k, v in leaves.items()}
+    finally:
+        ak.config.clear(); ak.config.update(old)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("cfg", [dict(), dict(ckpt_interval=30, shots_per_group=1)])
+def test_golden_records_and_gradients(golden_dir, name, cfg):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    for tag, use in (("stress", ("txx", "tzz", "txz")), ("vel", ("vx", "vz"))):
+        rec, grads = _run(g, use, **cfg)
+        for k in COMPS:
+            got = rec[k].detach().cpu().numpy()
+            assert rel_l2(got, g["rec_" + k]) <= REC_TOL, (name, k)
+            assert np.array_equal(got, g["rec_" + k]), f"{name}: record {k} not bit-identical to the reference"
+        for k in PLANES:
+            e = rel_l2(grads[k], g[f"g_{k}_{tag}"])
+            assert e <= GRAD_TOL and e <= 2e-5, (name, tag, k, e)
+    for k in COMPS:
+        assert rel_l2(rec["forward_wavefield_" + k].cpu().numpy(), g["fw_" + k]) <= 1e-5, (name, k)
+
+
+@pytest.mark.parametrize("name", ["elastic_pml_o4_fs", "elastic_gerjan_o6_nofs"])
+def test_model_level_gradients(golden_dir, name):
+    """vp / vs / rho / eps / delta gradients through ElasticPropagator + the torch parameterisation."""
+    from adfwi_b200 import synthetic as syn
+    from adfwi_b200.propagator import ElasticPropagator
+    g = np.load(f"{golden_dir}/{name}.npz")
+    dev = torch.device("cuda:0")
+    abc = str(g["abc"])
+    model = syn.ElasticGridModel(g["vp"], g["vs"], g["rho"], eps=g["eps"], delta=g["delta"], dx=float(g["dx"]), dz=float(g["dz"]),
+                                 nabc=int(g["nabc"]), free_surface=bool(g["free_surface"]), abc_type=abc,
+                                 requires_grad=("vp", "vs", "rho", "eps", "delta"), device=dev)
+    src = syn.Source(np.stack([g["src_x"], g["src_z"]], 1), g["src_v"], int(g["nt"]), float(g["dt"]), 30.0, moment_tensor=g["mt"])
+    rcv = syn.Receiver(np.stack([g["rcv_x"], g["rcv_z"]], 1))
+    prop = ElasticPropagator(model, syn.Survey(src, rcv), device=dev)
+    if abc == "PML":   # the fixture's profiles (same formula, vmax of the fixture's vp)
+        prop.bcx, prop.bcz = torch.tensor(g["bcx"], device=dev), torch.tensor(g["bcz"], device=dev)
+    else:
+        prop.damp = torch.tensor(g["damp"], device=dev)
+    rec = prop.forward(fd_order=int(g["order"]), checkpoint_segments=int(g["segments"]))
+    sum((rec[k] * torch.tensor(g["W_" + k], device=dev)).sum() for k in ("txx", "tzz", "txz")).backward()
+    for k in ("vp", "vs", "rho", "eps", "delta"):
+        e = rel_l2(getattr(model, k).grad.cpu().numpy(), g[f"g_{k}_stress"])
+        assert e <= GRAD_TOL, (name, k, e)
