@@ -114,7 +114,7 @@ def cpu_gradient_sample(wl, ns, nt):
     sx = np.round(np.linspace(2, nx - 3, ns)).astype(np.int64); sz = np.ones(ns, np.int64)
     rx = np.round(np.linspace(0, nx - 1, wl["nr"])).astype(np.int64); rz = np.ones(wl["nr"], np.int64)
     wav = np.broadcast_to(syn.integrated_ricker(nt, wl["dt"], wl["f0"] * 4).astype(np.float32), (ns, nt)).copy()
-    O.lib()
+    O.lib().oracle_set_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1
     t0 = time.perf_counter()
     # one forward sweep (with history), residual-like cotangent from the records, one adjoint sweep
     O.acoustic_run(coef, nabc, True, wl["dt"], sx, sz, wav, rx, rz, g_rcv=lambda rec: (rec["p"], None, None),
@@ -320,6 +320,9 @@ def run_b200(args, wl):
 
 
 def main():
+    # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)

@@ -216,3 +216,11 @@ int oracle_acoustic_adjoint(const ac_dims *d, const float *a1, const float *a2, 
     free(lp); free(lu); free(lw); free(ga1); free(ga2);
     return 0;
 }
+
+/* bench.py helper: torchrun exports OMP_NUM_THREADS=1; the reference arm wants all host threads */
+#ifdef _OPENMP
+#include <omp.h>
+int oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int oracle_set_threads(int n) { (void)n; return 1; }
+#endif
