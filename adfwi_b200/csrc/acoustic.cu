@@ -11,6 +11,7 @@
 // position (z,x) and loops over the shots of its shot sub-group, so coefficient loads and the
 // read-modify-write of gradient / illumination planes are amortised over shots.
 #include "common.cuh"
+#include "acoustic_fused.h"
 
 namespace adfwi {
 
@@ -426,10 +427,25 @@ static int ac_forward_step(const AcPlan& P, cudaStream_t st, int sb, int se, int
 
 using namespace adfwi;
 
+// The fused TMA pipeline (acoustic_fused.cu) is the default; the generic kernels of this file run
+// when the density gradient is wanted (it needs the post-step pressure history) or when the caller
+// sets bit 0 of desc->reserved[0] (used by the tests to cross-check the two pipelines).
+static bool ac_use_fused(const adfwi_acoustic_desc* d)
+{
+#ifdef ADFWI_HOST_EMUL
+    (void)d; return false;
+#else
+    return !(d->save_history && d->need_g_alpha2) && !(d->reserved[0] & 1);
+#endif
+}
+
 extern "C" size_t adfwi_acoustic_workspace_bytes(const adfwi_acoustic_desc* desc)
 {
     AcPlan P;
     if (ac_make_plan(desc, nullptr, &P) != ADFWI_OK) return 0;
+#ifndef ADFWI_HOST_EMUL
+    if (ac_use_fused(desc)) return acf_workspace_bytes(desc);
+#endif
     return P.bytes;
 }
 
@@ -437,6 +453,9 @@ extern "C" int adfwi_acoustic_group_size(const adfwi_acoustic_desc* desc)
 {
     AcPlan P;
     if (ac_make_plan(desc, nullptr, &P) != ADFWI_OK) return 0;
+#ifndef ADFWI_HOST_EMUL
+    if (ac_use_fused(desc)) return acf_group_size(desc);
+#endif
     return P.G;
 }
 
@@ -454,8 +473,15 @@ extern "C" int adfwi_acoustic_forward(const adfwi_acoustic_desc* desc,
     if (rc) return rc;
     if (!alpha1 || !alpha2 || !kappa1 || !kappa2 || !kappa3 || !src_v || !src_x || !src_z || !workspace) return ADFWI_E_NULL;
     if (P.nr > 0 && (!rcv_x || !rcv_z || !rcv_p)) return ADFWI_E_NULL;
-    if (workspace_bytes < P.bytes) return ADFWI_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+#ifndef ADFWI_HOST_EMUL
+    if (ac_use_fused(desc)) {
+        if (workspace_bytes < acf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
+        const float* coef[5] = {alpha1, kappa1, alpha2, kappa2, kappa3};
+        return acf_forward(desc, coef, src_v, src_x, src_z, rcv_x, rcv_z, rcv_p, rcv_u, rcv_w, illum_p, illum_u, illum_w, workspace, st);
+    }
+#endif
+    if (workspace_bytes < P.bytes) return ADFWI_E_WORKSPACE;
     const AcGeom& g = P.g;
     const bool illum = illum_p || illum_u || illum_w;
     const int nt = g.nt;
@@ -523,8 +549,15 @@ extern "C" int adfwi_acoustic_backward(const adfwi_acoustic_desc* desc,
         return ADFWI_E_NULL;
     if (P.need_g2 && !g_alpha2) return ADFWI_E_NULL;
     if (P.nr > 0 && (!rcv_x || !rcv_z)) return ADFWI_E_NULL;
-    if (workspace_bytes < P.bytes) return ADFWI_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+#ifndef ADFWI_HOST_EMUL
+    if (ac_use_fused(desc)) {
+        if (workspace_bytes < acf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
+        const float* coef[5] = {alpha1, kappa1, alpha2, kappa2, kappa3};
+        return acf_backward(desc, coef, src_v, src_x, src_z, rcv_x, rcv_z, g_rcv_p, g_rcv_u, g_rcv_w, g_alpha1, g_src_v, workspace, st);
+    }
+#endif
+    if (workspace_bytes < P.bytes) return ADFWI_E_WORKSPACE;
     const AcGeom& g = P.g;
     const int nt = g.nt;
     const dim3 blk(64, 4);

@@ -28,6 +28,9 @@ config = {
     "memory_fraction": float(os.environ.get("ADFWI_B200_MEM_FRACTION", "0.85")),
     # shots advanced together inside the library (0 = library picks for L2 residency)
     "shots_per_group": int(os.environ.get("ADFWI_B200_SHOTS_PER_GROUP", "0")),
+    # True: run the generic one-cell-per-thread kernels instead of the fused TMA pipeline
+    # (cross-checks in the tests; the density gradient always uses the generic kernels)
+    "force_generic": os.environ.get("ADFWI_B200_GENERIC", "0") == "1",
 }
 
 
@@ -95,6 +98,7 @@ class AcousticFD(torch.autograd.Function):
         save = need[0] or need[1] or need[5]
         desc = make_desc(nzp, nxp, ns, nt, nr, nabc, free_surface, dt, n_segments, save,
                          0, need[1], config["shots_per_group"])
+        desc.reserved[0] = 1 if config["force_generic"] else 0
         with torch.cuda.device(dev):
             if save:
                 if config["ckpt_interval"] is not None:

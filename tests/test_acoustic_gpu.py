@@ -50,3 +50,70 @@ def test_golden_records_and_gradients(golden_dir, name, cfg):
         assert rel_l2(gv, g[f"g_v_{comp}"]) <= 2e-5 and rel_l2(grho, g[f"g_rho_{comp}"]) <= 2e-5
     for k in ("forward_wavefield_p", "forward_wavefield_u", "forward_wavefield_w"):
         assert rel_l2(rec[k].cpu().numpy(), g["rec_" + k]) <= 1e-5
+
+
+def _run_vp_only(g, comp, **cfg):
+    from adfwi_b200.propagator import acoustic_kernels as ak
+    old = dict(ak.config)
+    ak.config.update(cfg)
+    try:
+        dev = torch.device("cuda:0")
+        t = lambda k, **kw: torch.tensor(g[k], device=dev, **kw)
+        v = t("vp").requires_grad_(True)
+        rec = ak.forward_kernel(int(g["nx"]), int(g["nz"]), float(g["dx"]), float(g["dz"]), int(g["nt"]), float(g["dt"]),
+                                int(g["nabc"]), bool(g["free_surface"]), t("src_x"), t("src_z"), len(g["src_x"]),
+                                t("src_v"), t("rcv_x"), t("rcv_z"), len(g["rcv_x"]), t("damp"), v, t("rho"),
+                                checkpoint_segments=int(g["segments"]), device=dev, dtype=torch.float32)
+        (rec[comp] * t("W_" + comp)).sum().backward()
+        return rec, v.grad.cpu().numpy()
+    finally:
+        ak.config.clear(); ak.config.update(old)
+
+
+@pytest.mark.parametrize("name", ["acoustic_fs", "acoustic_nofs"])
+@pytest.mark.parametrize("cfg", [dict(), dict(ckpt_interval=40, shots_per_group=1), dict(ckpt_interval=64),
+                                 dict(force_generic=True)])
+def test_fused_pipeline_vp_only(golden_dir, name, cfg):
+    """vp-only gradients take the fused TMA pipeline (the default fast path); force_generic
+    cross-checks the generic kernels on the same inputs."""
+    g = np.load(f"{golden_dir}/{name}.npz")
+    for comp in "puw":
+        rec, gv = _run_vp_only(g, comp, **cfg)
+        for k in "puw":
+            got = rec[k].detach().cpu().numpy()
+            assert np.array_equal(got, g["rec_" + k]), f"{name}: record {k} not bit-identical to the reference"
+        e = rel_l2(gv, g[f"g_v_{comp}"])
+        assert e <= GRAD_TOL and e <= 2e-5, (name, comp, e)
+    for k in ("forward_wavefield_p", "forward_wavefield_u", "forward_wavefield_w"):
+        assert rel_l2(rec[k].cpu().numpy(), g["rec_" + k]) <= 1e-5
+
+
+def test_fused_large_grid_matches_generic():
+    """Multi-tile grid (several 64x32 tiles, ragged edges, many receivers): fused vs generic kernels."""
+    from adfwi_b200.propagator import acoustic_kernels as ak
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    nz, nx, nabc, nt, ns = 83, 149, 12, 120, 3
+    v = (1800 + 1500 * torch.rand(nz, nx, device=dev))
+    rho = 2000 + 200 * torch.rand(nz, nx, device=dev)
+    damp = 30 * torch.rand(nz + 2 * nabc, nx + 2 * nabc, device=dev)
+    sx = torch.tensor([3, 70, 140], device=dev); sz = torch.tensor([0, 40, 2], device=dev)
+    rx = torch.arange(0, nx, 2, device=dev); rz = torch.cat([torch.zeros(40, dtype=torch.long), torch.full((35,), 50)]).to(dev)
+    src = torch.randn(ns, nt, device=dev)
+    W = torch.randn(ns, nt, rx.numel(), device=dev)
+    out = {}
+    for fs in (True, False):
+        for mode in (False, True):
+            old = dict(ak.config); ak.config.update(force_generic=mode, shots_per_group=2)
+            try:
+                vv = v.clone().requires_grad_(True)
+                rec = ak.forward_kernel(nx, nz, 10.0, 10.0, nt, 1e-3, nabc, fs, sx, sz, ns, src, rx, rz, rx.numel(), damp, vv, rho, device=dev)
+                ((rec["p"] * W).sum() + 1e6 * (rec["u"] * W).sum() + 1e6 * (rec["w"] * W).sum()).backward()
+                out[mode] = (rec, vv.grad.clone())
+            finally:
+                ak.config.clear(); ak.config.update(old)
+        for k in ("p", "u", "w"):
+            assert torch.equal(out[False][0][k], out[True][0][k]), (fs, k)
+        for k in ("forward_wavefield_p", "forward_wavefield_u", "forward_wavefield_w"):
+            assert rel_l2(out[False][0][k].cpu().numpy(), out[True][0][k].cpu().numpy()) < 1e-5
+        assert rel_l2(out[False][1].cpu().numpy(), out[True][1].cpu().numpy()) < 1e-5, fs
