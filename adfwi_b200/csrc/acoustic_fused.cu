@@ -6,19 +6,25 @@
 //   ac_adj_fused : receiver-cotangent injection + the whole reverse step 7T..1T of SURVEY.md
 //                  Appendix A.1 + g_alpha1 accumulation + g_src
 //
-// Design (v2, "lean"):
-//   * A CTA of 128 threads owns one 64(x) x 32(z) tile of one shot at a time (persistent loop over
-//     (tile, shot) items, shot-minor so concurrently running CTAs share coefficient lines in L2).
-//   * The old p,u,w (or lambda) tiles with their halos (4 cells in x, 3 in z) are brought into
-//     shared memory by TMA (cp.async.bulk.tensor.3d, hardware zero fill outside the grid).
+// Design (v3, "tile-persistent"):
+//   * A CTA of 128 threads owns one 64(x) x 32(z) tile and walks through a chunk of the group's
+//     shots.  Everything that does not depend on the shot stays on chip for the whole walk: the
+//     coefficients of the thread's cells live in REGISTERS (loaded once per tile), the
+//     illumination / gradient sums accumulate in registers and are flushed once per tile with
+//     128-bit reductions (red.global.add.v4.f32).
+//   * Per shot, the old p,u,w (or lambda) tiles with their halos (4 cells in x, 3 in z) are
+//     brought into shared memory by TMA (cp.async.bulk.tensor.3d, hardware zero fill outside the
+//     grid) into a double buffer: the loads of shot s+1 are in flight while shot s is computed,
+//     so the inner loop never waits on a global load.
 //   * Phase 1 computes the intermediate field (new pressure / pressure cotangent) on the tile plus
-//     the one/two-cell ring phase 2 needs (halo recompute); every thread owns a float4 of 4 cells
-//     in x and a block of 5 rows in z, so all shared-memory traffic is 64/128-bit and the z
-//     neighbours are reused from registers.  Phase 2 (4 cells x 4 rows per thread) produces the
-//     new fields and writes them with 128-bit stores to the other buffer of a ping-pong pair.
+//     the ring phase 2 needs (halo recompute); every thread owns a float4 of 4 cells in x and a
+//     block of 5 rows in z, so all shared-memory traffic is 64/128-bit and the z neighbours are
+//     reused from registers.  Phase 2 (4 cells x 4 rows per thread) produces the new fields and
+//     writes them with 128-bit stores to the other buffer of a ping-pong pair.
 //   * No per-cell region predicates: the update regions of Appendix A.1 are folded into a private,
 //     zero-padded copy of the coefficient planes ("coefficient pack": alpha = 0 and kappa = 0
-//     outside a field's update region make the update the identity, bit for bit).
+//     outside a field's update region make the update the identity, bit for bit).  Tiles whose
+//     neighbourhood has no damping at all run a variant without the kappa terms (1.0f*x == x).
 //   * Receivers are bucketed per tile once per call; a tile only touches its own receivers.
 // Same arithmetic and association as the generic kernels in acoustic.cu (-fmad=false): forward
 // records stay bit-identical to the CPU reference.
@@ -42,10 +48,12 @@ constexpr int NGP = NG + 2;                 // + one side group left and right (
 constexpr int RB = 5;                       // rows per phase-1 block
 constexpr int NB1 = (TZ + 3) / RB;          // phase-1 row blocks: rows [-1, TZ+2)
 constexpr int NTHREADS = NG * (TZ / 4);     // 128
+constexpr int CMAX = 32;                    // max shots per chunk (per-shot scalars staged in shared memory)
 static_assert((TZ + 3) % RB == 0, "phase-1 row blocks must tile rows [-1,TZ+2)");
 static_assert(NGP * NB1 <= NTHREADS, "phase 1 must fit one pass");
-static_assert(RX <= NTHREADS, "row fix-ups use one thread per staged column");
+static_assert(RX <= NTHREADS && CMAX <= NTHREADS, "row fix-ups / scalar staging use one thread per element");
 constexpr int RECT_BYTES = ((RZ * RX * 4 + 127) / 128) * 128;   // 11008
+constexpr int STAGE_BYTES = 3 * RECT_BYTES;                      // p,u,w of one shot
 constexpr int CPX = 8, CPZ = 4;             // apron of the coefficient pack (cells)
 
 struct FGeom {
@@ -62,25 +70,25 @@ struct CoefPack { const float *a1, *k1, *a2u, *k2, *a2w, *k3; };
 struct RcvBuckets { const int* start; const int* id; const int* zx; const unsigned char* nbr; };
 
 struct FwdArgs {
-    CoefPack cp;
+    CoefPack cp; const unsigned char* tflags;
     float *p_out, *u_out, *w_out;
     const float* src_v; const int64_t *sx, *sz;
     float* hist; int hist_len, tl, it;
     int nr; RcvBuckets rb;
     float *rcv_p, *rcv_u, *rcv_w;
     float *ill_p, *ill_u; int acc_u;
-    int s_begin, s_end;
+    int s_begin, s_end, chunk, nchunks;
 };
 
 struct AdjArgs {
-    CoefPack cp;
+    CoefPack cp; const unsigned char* tflags;
     float *lp_out, *lu_out, *lw_out;
     const int64_t *sx, *sz;
     const float* hist; int hist_len, tl, it;
     int nr; RcvBuckets rb;
     const float *gp, *gu, *gw;
     float* g1part; float* g_src;
-    int s_begin, s_end;
+    int s_begin, s_end, chunk, nchunks;
 };
 
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
@@ -96,75 +104,112 @@ __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ void red4(float* p, const float4& v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 one_minus(const float4& k) { return make_float4(1.0f - k.x, 1.0f - k.y, 1.0f - k.z, 1.0f - k.w); }
+__device__ __forceinline__ float4 neg4(const float4& k) { return make_float4(-k.x, -k.y, -k.z, -k.w); }
+
+// thread roles shared by both kernels
+struct Roles {
+    int b1, gi1, c01, r01, so1; bool p1_active;    // phase 1: float4 group gi1 in [-1,NG], row block b1
+    int q2, l2, c02, r02, so2;                     // phase 2: float4 group l2, row quad q2
+    __device__ __forceinline__ explicit Roles(int tid)
+    {
+        b1 = tid / NGP; gi1 = tid - b1 * NGP - 1; p1_active = tid < NGP * NB1;
+        c01 = 4 * gi1; r01 = RB * b1 - 1; so1 = (r01 + HZ) * RX + c01 + HX;
+        q2 = tid / NG; l2 = tid - q2 * NG; c02 = 4 * l2; r02 = 4 * q2; so2 = (r02 + HZ) * RX + c02 + HX;
+    }
+};
 
 // ------------------------------------------------------------------------------------------
-template <bool FS, bool SAVE, bool ILLUM>
-__global__ void __launch_bounds__(NTHREADS, 5)
-ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_u,
-             const __grid_constant__ CUtensorMap tm_w, const FGeom g, const FwdArgs a)
+// forward: one tile, shots [s_lo, s_hi)
+// ------------------------------------------------------------------------------------------
+template <bool FS, bool SAVE, bool ILLUM, bool PML>
+__device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensorMap* tm_u, const CUtensorMap* tm_w,
+                                         const FGeom& g, const FwdArgs& a, unsigned char* smem_raw, uint64_t* bar,
+                                         uint32_t& par, int* s_sz, int* s_sx, float* s_sv,
+                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* ps = (float*)smem_raw;
-    float* us = (float*)(smem_raw + RECT_BYTES);
-    float* ws = (float*)(smem_raw + 2 * RECT_BYTES);
-    float* pn = (float*)(smem_raw + 3 * RECT_BYTES);
-    uint64_t* bar = (uint64_t*)(smem_raw + 4 * RECT_BYTES);
-    const int tid = threadIdx.x;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    const int nsh = a.s_end - a.s_begin;
-    const int nitems = g.ntx * g.ntz * nsh;
-    uint32_t parity = 0;
+    float* pn = (float*)(smem_raw + 2 * STAGE_BYTES);
     const int ld = g.ld, cpld = g.cpld;
     const float c1 = g.c1, c2 = g.c2;
-    // phase-1 role: float4 group gi in [-1, NG], row block b in [0, NB1)
-    const int b1 = tid / NGP, gi1 = tid - b1 * NGP - 1;
-    const bool p1_active = tid < NGP * NB1;
-    const int c01 = 4 * gi1, r01 = RB * b1 - 1;
-    const int so1 = (r01 + HZ) * RX + c01 + HX;
-    // phase-2 role: float4 group l, row quad q
-    const int q2 = tid / NG, l2 = tid - q2 * NG;
-    const int c02 = 4 * l2, r02 = 4 * q2;
-    const int so2 = (r02 + HZ) * RX + c02 + HX;
-
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int sl = item % nsh, tile = item / nsh;
-        const int s = a.s_begin + sl;
-        const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
-        const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
-        if (tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(bar, 3 * RZ * RX * 4);
-            tma_load_3d(ps, &tm_p, X0 - HX, Z0 - HZ, s, bar);
-            tma_load_3d(us, &tm_u, X0 - HX, Z0 - HZ, s, bar);
-            tma_load_3d(ws, &tm_w, X0 - HX, Z0 - HZ, s, bar);
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
+    // ---- prologue: start the first two shots' loads, stage per-shot scalars, load coefficients -----
+    if (tid == 0) {
+        fence_proxy_async();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (s_lo + k < s_hi) {
+                float* st = (float*)(smem_raw + k * STAGE_BYTES);
+                mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
+                tma_load_3d(st, tm_p, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
+                tma_load_3d(st + RECT_BYTES / 4, tm_u, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
+                tma_load_3d(st + 2 * RECT_BYTES / 4, tm_w, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
+            }
+    }
+    if (tid < s_hi - s_lo) {
+        const int s = s_lo + tid;
+        s_sz[tid] = (int)a.sz[s]; s_sx[tid] = (int)a.sx[s];
+        s_sv[tid] = g.dt * a.src_v[(size_t)s * g.nt + a.it];
+    }
+    const int gz1 = Z0 + R.r01, gx1 = X0 + R.c01;
+    const int gz2 = Z0 + R.r02, gx2 = X0 + R.c02;
+    float4 A1[RB], T1[RB];
+    if (R.p1_active) {
+        const ptrdiff_t cpo = (ptrdiff_t)gz1 * cpld + gx1;       // may be negative: the pack has an apron
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            A1[j] = ldg4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld);
+            if (PML) T1[j] = one_minus(ldg4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld));
         }
-        const int szs = (int)a.sz[s], sxs = (int)a.sx[s];
+    }
+    float4 AU[4], AW[4], T2[4], T3[4];
+    {
+        const ptrdiff_t cpo = (ptrdiff_t)gz2 * cpld + gx2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            AU[j] = ldg4(a.cp.a2u + cpo + (ptrdiff_t)j * cpld);
+            if (PML) {
+                AW[j] = ldg4(a.cp.a2w + cpo + (ptrdiff_t)j * cpld);
+                T2[j] = one_minus(ldg4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld));
+                T3[j] = one_minus(ldg4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld));
+            }
+        }
+    }
+    float4 accp[4], accu[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { accp[j] = make_float4(0.f, 0.f, 0.f, 0.f); accu[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
+    const bool has_rcv = rcv_hi > rcv_lo;
+    const bool col1ok = (R.gi1 >= 0) && (R.gi1 < NG) && (gx1 < ld);
+    const bool col2ok = gx2 < ld;
+    __syncthreads();          // s_sz/s_sx/s_sv visible
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = (s - s_lo) & 1;
+        const float* ps = (const float*)(smem_raw + k * STAGE_BYTES);
+        float* us = (float*)(smem_raw + k * STAGE_BYTES + RECT_BYTES);
+        float* ws = (float*)(smem_raw + k * STAGE_BYTES + 2 * RECT_BYTES);
+        const int szs = s_sz[s - s_lo], sxs = s_sx[s - s_lo];
         const bool has_src = (szs >= Z0 - 1) && (szs < Z0 + TZ + 2) && (sxs >= X0 - 1) && (sxs < X0 + TX + 2);
-        const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
-        const bool has_rcv = rcv_hi > rcv_lo;
-        while (!mbar_try(bar, parity)) {}
-        parity ^= 1;
+        while (!mbar_try(bar + k, (par >> k) & 1u)) {}
+        par ^= 1u << k;
         // ---- phase 1: new pressure on rows [-1,TZ+2) x cols [-4,TX+4) (cols [-1,TX+2) are used) ----
-        if (p1_active) {
-            const int gz0 = Z0 + r01, gx0 = X0 + c01;
-            const size_t cpo = (size_t)gz0 * cpld + gx0;      // may be "negative": the pack has an apron
-            const float* A1 = a.cp.a1 + (ptrdiff_t)cpo;
-            const float* K1 = a.cp.k1 + (ptrdiff_t)cpo;
+        if (R.p1_active) {
             float4 wq[RB + 3];
 #pragma unroll
-            for (int k = 0; k < RB + 3; ++k) wq[k] = ld4(ws + so1 + (k - 2) * RX);
+            for (int q = 0; q < RB + 3; ++q) wq[q] = ld4(ws + R.so1 + (q - 2) * RX);
             float4 pv[RB];
-            const bool colok = (gi1 >= 0) && (gi1 < NG) && (gx0 < ld);
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
-                const float* ur = us + so1 + j * RX;
+                const float* ur = us + R.so1 + j * RX;
                 const float2 ul = ld2(ur - 2);
                 const float4 um = ld4(ur);
                 const float uR = ur[4];
-                const float4 po = ld4(ps + so1 + j * RX);
-                const float4 al = ldg4(A1 + (size_t)j * cpld);
-                const float4 kk = ldg4(K1 + (size_t)j * cpld);
+                const float4 po = ld4(ps + R.so1 + j * RX);
                 const float4 w0 = wq[j + 2], wm1 = wq[j + 1], wp1 = wq[j + 3], wm2 = wq[j];
                 float4 S;
                 S.x = c1 * (((um.x - ul.y) + w0.x) - wm1.x) + c2 * (((um.y - ul.x) + wp1.x) - wm2.x);
@@ -172,19 +217,22 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
                 S.z = c1 * (((um.z - um.y) + w0.z) - wm1.z) + c2 * (((um.w - um.x) + wp1.z) - wm2.z);
                 S.w = c1 * (((um.w - um.z) + w0.w) - wm1.w) + c2 * (((uR - um.y) + wp1.w) - wm2.w);
                 if (SAVE) {
-                    const int r = r01 + j, gz = gz0 + j;
-                    if (colok && r >= 0 && r < TZ && gz < g.nzp)
-                        __stcs(reinterpret_cast<float4*>(a.hist + ((size_t)s * a.hist_len + a.tl) * g.plane + (size_t)gz * ld + gx0), S);
+                    const int r = R.r01 + j, gz = gz1 + j;
+                    if (col1ok && r >= 0 && r < TZ && gz < g.nzp)
+                        __stcs(reinterpret_cast<float4*>(a.hist + ((size_t)s * a.hist_len + a.tl) * g.plane + (size_t)gz * ld + gx1), S);
                 }
-                pv[j].x = (1.0f - kk.x) * po.x - al.x * S.x;
-                pv[j].y = (1.0f - kk.y) * po.y - al.y * S.y;
-                pv[j].z = (1.0f - kk.z) * po.z - al.z * S.z;
-                pv[j].w = (1.0f - kk.w) * po.w - al.w * S.w;
+                if (PML) {
+                    pv[j].x = T1[j].x * po.x - A1[j].x * S.x; pv[j].y = T1[j].y * po.y - A1[j].y * S.y;
+                    pv[j].z = T1[j].z * po.z - A1[j].z * S.z; pv[j].w = T1[j].w * po.w - A1[j].w * S.w;
+                } else {
+                    pv[j].x = po.x - A1[j].x * S.x; pv[j].y = po.y - A1[j].y * S.y;
+                    pv[j].z = po.z - A1[j].z * S.z; pv[j].w = po.w - A1[j].w * S.w;
+                }
             }
             if (has_src) {     // p[sz,sx] += dt*src   (acoustic_kernels.py:131-132)
-                const int dr = szs - gz0, dc = sxs - gx0;
+                const int dr = szs - gz1, dc = sxs - gx1;
                 if (dr >= 0 && dr < RB && dc >= 0 && dc < 4) {
-                    const float srcval = g.dt * a.src_v[(size_t)s * g.nt + a.it];
+                    const float srcval = s_sv[s - s_lo];
 #pragma unroll
                     for (int j = 0; j < RB; ++j) {
                         if (j == dr) {
@@ -196,65 +244,60 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
                     }
                 }
             }
-            if (FS && tzi == 0 && b1 == 0) {      // p[fs-1] = -p[fs+1]: tile rows 0 and 2 = block rows 1 and 3
+            if (FS && tzi == 0 && R.b1 == 0) {      // p[fs-1] = -p[fs+1]: tile rows 0 and 2 = block rows 1 and 3
                 pv[1].x = -pv[3].x; pv[1].y = -pv[3].y; pv[1].z = -pv[3].z; pv[1].w = -pv[3].w;
             }
 #pragma unroll
-            for (int j = 0; j < RB; ++j) st4(pn + so1 + j * RX, pv[j]);
+            for (int j = 0; j < RB; ++j) st4(pn + R.so1 + j * RX, pv[j]);
         }
         __syncthreads();
         // ---- phase 2: velocities on the interior, stores, illumination -----------------------------
         {
-            const int gx0 = X0 + c02, gz0 = Z0 + r02;
-            const bool colok = gx0 < ld;
-            const size_t cpo = (size_t)gz0 * cpld + gx0;
             float4 P[7];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) P[k] = ld4(pn + so2 + (k - 1) * RX);
+            for (int q = 0; q < 7; ++q) P[q] = ld4(pn + R.so2 + (q - 1) * RX);
             float4 uv[4], wv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float* pr = pn + so2 + j * RX;
+                const float* pr = pn + R.so2 + j * RX;
                 const float pL = pr[-1];
                 const float2 pR = ld2(pr + 4);
                 const float4 p0 = P[j + 1], pm1 = P[j], pp1 = P[j + 2], pp2 = P[j + 3];
-                const float4 uo = ld4(us + so2 + j * RX), wo = ld4(ws + so2 + j * RX);
-                const float4 au = ldg4(a.cp.a2u + (ptrdiff_t)cpo + (size_t)j * cpld), k2 = ldg4(a.cp.k2 + (ptrdiff_t)cpo + (size_t)j * cpld);
-                const float4 aw = ldg4(a.cp.a2w + (ptrdiff_t)cpo + (size_t)j * cpld), k3 = ldg4(a.cp.k3 + (ptrdiff_t)cpo + (size_t)j * cpld);
-                uv[j].x = (1.0f - k2.x) * uo.x - au.x * (c1 * (p0.y - p0.x) + c2 * (p0.z - pL));
-                uv[j].y = (1.0f - k2.y) * uo.y - au.y * (c1 * (p0.z - p0.y) + c2 * (p0.w - p0.x));
-                uv[j].z = (1.0f - k2.z) * uo.z - au.z * (c1 * (p0.w - p0.z) + c2 * (pR.x - p0.y));
-                uv[j].w = (1.0f - k2.w) * uo.w - au.w * (c1 * (pR.x - p0.w) + c2 * (pR.y - p0.z));
-                wv[j].x = (1.0f - k3.x) * wo.x - aw.x * (c1 * (pp1.x - p0.x) + c2 * (pp2.x - pm1.x));
-                wv[j].y = (1.0f - k3.y) * wo.y - aw.y * (c1 * (pp1.y - p0.y) + c2 * (pp2.y - pm1.y));
-                wv[j].z = (1.0f - k3.z) * wo.z - aw.z * (c1 * (pp1.z - p0.z) + c2 * (pp2.z - pm1.z));
-                wv[j].w = (1.0f - k3.w) * wo.w - aw.w * (c1 * (pp1.w - p0.w) + c2 * (pp2.w - pm1.w));
+                const float4 uo = ld4(us + R.so2 + j * RX), wo = ld4(ws + R.so2 + j * RX);
+                const float4 au = AU[j], aw = PML ? AW[j] : AU[j];
+                float4 du, dw;
+                du.x = au.x * (c1 * (p0.y - p0.x) + c2 * (p0.z - pL));
+                du.y = au.y * (c1 * (p0.z - p0.y) + c2 * (p0.w - p0.x));
+                du.z = au.z * (c1 * (p0.w - p0.z) + c2 * (pR.x - p0.y));
+                du.w = au.w * (c1 * (pR.x - p0.w) + c2 * (pR.y - p0.z));
+                dw.x = aw.x * (c1 * (pp1.x - p0.x) + c2 * (pp2.x - pm1.x));
+                dw.y = aw.y * (c1 * (pp1.y - p0.y) + c2 * (pp2.y - pm1.y));
+                dw.z = aw.z * (c1 * (pp1.z - p0.z) + c2 * (pp2.z - pm1.z));
+                dw.w = aw.w * (c1 * (pp1.w - p0.w) + c2 * (pp2.w - pm1.w));
+                if (PML) {
+                    uv[j].x = T2[j].x * uo.x - du.x; uv[j].y = T2[j].y * uo.y - du.y; uv[j].z = T2[j].z * uo.z - du.z; uv[j].w = T2[j].w * uo.w - du.w;
+                    wv[j].x = T3[j].x * wo.x - dw.x; wv[j].y = T3[j].y * wo.y - dw.y; wv[j].z = T3[j].z * wo.z - dw.z; wv[j].w = T3[j].w * wo.w - dw.w;
+                } else {
+                    uv[j].x = uo.x - du.x; uv[j].y = uo.y - du.y; uv[j].z = uo.z - du.z; uv[j].w = uo.w - du.w;
+                    wv[j].x = wo.x - dw.x; wv[j].y = wo.y - dw.y; wv[j].z = wo.z - dw.z; wv[j].w = wo.w - dw.w;
+                }
             }
-            if (FS && tzi == 0 && q2 == 0) wv[0] = wv[1];        // w[fs-1] = w[fs]   (acoustic_kernels.py:163-164)
+            if (FS && tzi == 0 && R.q2 == 0) wv[0] = wv[1];        // w[fs-1] = w[fs]   (acoustic_kernels.py:163-164)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int gz = gz0 + j;
-                if (colok && gz < g.nzp) {
-                    const size_t cg = (size_t)gz * ld + gx0;
-                    const size_t o = (size_t)s * g.plane + cg;
-                    const float4 p0 = P[j + 1];
+                const int gz = gz2 + j;
+                const float4 p0 = P[j + 1];
+                if (col2ok && gz < g.nzp) {
+                    const size_t o = (size_t)s * g.plane + (size_t)gz * ld + gx2;
                     st4(a.p_out + o, p0);
                     st4(a.u_out + o, uv[j]);
                     st4(a.w_out + o, wv[j]);
-                    if (ILLUM) {      // per-shot-slot partial sums over the whole plane; cropped when finalised
-                        float* ip = a.ill_p + (size_t)sl * g.plane + cg;
-                        float4 acc = ld4(ip);
-                        acc.x += p0.x * p0.x; acc.y += p0.y * p0.y; acc.z += p0.z * p0.z; acc.w += p0.w * p0.w;
-                        st4(ip, acc);
-                        if (a.acc_u) {
-                            float* iu = a.ill_u + (size_t)sl * g.plane + cg;
-                            float4 au = ld4(iu);
-                            au.x += uv[j].x * uv[j].x; au.y += uv[j].y * uv[j].y; au.z += uv[j].z * uv[j].z; au.w += uv[j].w * uv[j].w;
-                            st4(iu, au);
-                        }
-                    }
                 }
-                if (has_rcv) { st4(us + so2 + j * RX, uv[j]); st4(ws + so2 + j * RX, wv[j]); }
+                if (ILLUM) {      // summed over the chunk's shots in registers; cropped when finalised
+                    accp[j].x += p0.x * p0.x; accp[j].y += p0.y * p0.y; accp[j].z += p0.z * p0.z; accp[j].w += p0.w * p0.w;
+                    accu[j].x += uv[j].x * uv[j].x; accu[j].y += uv[j].y * uv[j].y; accu[j].z += uv[j].z * uv[j].z; accu[j].w += uv[j].w * uv[j].w;
+                }
+                if (has_rcv) { st4(us + R.so2 + j * RX, uv[j]); st4(ws + R.so2 + j * RX, wv[j]); }
             }
         }
         // ---- receivers of this tile (acoustic_kernels.py:167-169) ----------------------------------
@@ -268,56 +311,138 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
                 if (a.rcv_u) a.rcv_u[o] = us[off];
                 if (a.rcv_w) a.rcv_w[o] = ws[off];
             }
+            fence_proxy_async();      // generic-proxy writes to the stage precede its TMA refill
         }
         __syncthreads();
+        if (tid == 0 && s + 2 < s_hi) {       // refill this stage with shot s+2 while shot s+1 is computed
+            float* st = (float*)(smem_raw + k * STAGE_BYTES);
+            fence_proxy_async();
+            mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
+            tma_load_3d(st, tm_p, X0 - HX, Z0 - HZ, s + 2, bar + k);
+            tma_load_3d(st + RECT_BYTES / 4, tm_u, X0 - HX, Z0 - HZ, s + 2, bar + k);
+            tma_load_3d(st + 2 * RECT_BYTES / 4, tm_w, X0 - HX, Z0 - HZ, s + 2, bar + k);
+        }
+    }
+    if (ILLUM) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gz = gz2 + j;
+            if (col2ok && gz < g.nzp) {
+                const size_t cg = (size_t)chunk * g.plane + (size_t)gz * ld + gx2;
+                red4(a.ill_p + cg, accp[j]);
+                if (a.acc_u) red4(a.ill_u + cg, accu[j]);
+            }
+        }
+    }
+}
+
+template <bool FS, bool SAVE, bool ILLUM>
+__global__ void __launch_bounds__(NTHREADS, 2)
+ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_u,
+             const __grid_constant__ CUtensorMap tm_w, const FGeom g, const FwdArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = (uint64_t*)(smem_raw + 2 * STAGE_BYTES + RECT_BYTES);
+    int* s_sz = (int*)(bar + 2);
+    int* s_sx = s_sz + CMAX;
+    float* s_sv = (float*)(s_sx + CMAX);
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    const int nitems = g.ntx * g.ntz * a.nchunks;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
+        const int s_lo = a.s_begin + chunk * a.chunk;
+        const int s_hi = min(s_lo + a.chunk, a.s_end);
+        if (a.tflags[tile]) fwd_tile<FS, SAVE, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
+        else                fwd_tile<FS, SAVE, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
+        __syncthreads();      // per-shot scalars and stages are reused by the next item
     }
 }
 
 // ------------------------------------------------------------------------------------------
-template <bool FS>
-__global__ void __launch_bounds__(NTHREADS, 4)
-ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ CUtensorMap tm_lu,
-             const __grid_constant__ CUtensorMap tm_lw, const FGeom g, const AdjArgs a)
+// adjoint: one tile, shots [s_lo, s_hi)
+// ------------------------------------------------------------------------------------------
+template <bool FS, bool PML>
+__device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw,
+                                         const FGeom& g, const AdjArgs& a, unsigned char* smem_raw, uint64_t* bar,
+                                         uint32_t& par, int* s_sz, int* s_sx,
+                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* lps = (float*)smem_raw;
-    float* lus = (float*)(smem_raw + RECT_BYTES);
-    float* lws = (float*)(smem_raw + 2 * RECT_BYTES);
-    float* lp1 = (float*)(smem_raw + 3 * RECT_BYTES);     // lambda_p after undoing W,U (and 3T)
-    float* mps = (float*)(smem_raw + 4 * RECT_BYTES);     // m = -alpha1 * lambda_p1
-    uint64_t* bar = (uint64_t*)(smem_raw + 5 * RECT_BYTES);
-    const int tid = threadIdx.x;
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    const int nsh = a.s_end - a.s_begin;
-    const int nitems = g.ntx * g.ntz * nsh;
-    const bool have_g = a.nr > 0 && (a.gp || a.gu || a.gw);
-    uint32_t parity = 0;
+    float* lp1 = (float*)(smem_raw + 2 * STAGE_BYTES);                  // lambda_p after undoing W,U (and 3T)
+    float* mps = (float*)(smem_raw + 2 * STAGE_BYTES + RECT_BYTES);     // m = -alpha1 * lambda_p1
     const int ld = g.ld, cpld = g.cpld;
     const float c1 = g.c1, c2 = g.c2;
-    const int b1 = tid / NGP, gi1 = tid - b1 * NGP - 1;
-    const bool p1_active = tid < NGP * NB1;
-    const int c01 = 4 * gi1, r01 = RB * b1 - 1;
-    const int so1 = (r01 + HZ) * RX + c01 + HX;
-    const int q2 = tid / NG, l2 = tid - q2 * NG;
-    const int c02 = 4 * l2, r02 = 4 * q2;
-    const int so2 = (r02 + HZ) * RX + c02 + HX;
-
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int sl = item % nsh, tile = item / nsh;
-        const int s = a.s_begin + sl;
-        const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
-        const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
-        if (tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(bar, 3 * RZ * RX * 4);
-            tma_load_3d(lps, &tm_lp, X0 - HX, Z0 - HZ, s, bar);
-            tma_load_3d(lus, &tm_lu, X0 - HX, Z0 - HZ, s, bar);
-            tma_load_3d(lws, &tm_lw, X0 - HX, Z0 - HZ, s, bar);
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
+    const bool have_g = a.nr > 0 && (a.gp || a.gu || a.gw);
+    if (tid == 0) {
+        fence_proxy_async();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (s_lo + k < s_hi) {
+                float* st = (float*)(smem_raw + k * STAGE_BYTES);
+                mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
+                tma_load_3d(st, tm_lp, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
+                tma_load_3d(st + RECT_BYTES / 4, tm_lu, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
+                tma_load_3d(st + 2 * RECT_BYTES / 4, tm_lw, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
+            }
+    }
+    if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
+    const int gz1 = Z0 + R.r01, gx1 = X0 + R.c01;
+    const int gz2 = Z0 + R.r02, gx2 = X0 + R.c02;
+    // phase-1 coefficients: -alpha2w rows r01-2..r01+5 (own columns), -alpha2u columns c01-2..c01+4 of
+    // the five rows, -alpha1 of the five rows
+    float4 NAW[RB + 3], NA1[RB];
+    float NAU[RB][7];
+    if (R.p1_active) {
+        const ptrdiff_t cpo = (ptrdiff_t)gz1 * cpld + gx1;
+#pragma unroll
+        for (int q = 0; q < RB + 3; ++q) NAW[q] = neg4(ldg4(a.cp.a2w + cpo + (ptrdiff_t)(q - 2) * cpld));
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const float* ar = a.cp.a2u + cpo + (ptrdiff_t)j * cpld;
+            const float2 al = ldg2(ar - 2); const float4 am = ldg4(ar); const float aR = __ldg(ar + 4);
+            NAU[j][0] = -al.x; NAU[j][1] = -al.y; NAU[j][2] = -am.x; NAU[j][3] = -am.y; NAU[j][4] = -am.z; NAU[j][5] = -am.w; NAU[j][6] = -aR;
+            NA1[j] = neg4(ldg4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld));
         }
-        const bool inject = have_g && a.rb.nbr[tile];
-        while (!mbar_try(bar, parity)) {}
-        parity ^= 1;
+    }
+    float4 T1[4], T2[4], T3[4];
+    if (PML) {
+        const ptrdiff_t cpo = (ptrdiff_t)gz2 * cpld + gx2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            T1[j] = one_minus(ldg4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld));
+            T2[j] = one_minus(ldg4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld));
+            T3[j] = one_minus(ldg4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld));
+        }
+    }
+    float4 gacc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool inject = have_g && a.rb.nbr[tile];
+    const bool col2ok = gx2 < ld;
+    __syncthreads();
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = (s - s_lo) & 1;
+        float* lps = (float*)(smem_raw + k * STAGE_BYTES);
+        float* lus = (float*)(smem_raw + k * STAGE_BYTES + RECT_BYTES);
+        float* lws = (float*)(smem_raw + k * STAGE_BYTES + 2 * RECT_BYTES);
+        // the stencil history of this step does not depend on anything computed here: fetch it early
+        float4 Sh[4];
+        {
+            const float* Hs = a.hist + ((size_t)s * a.hist_len + a.tl) * g.plane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gz = gz2 + j;
+                Sh[j] = (col2ok && gz < g.nzp) ? __ldcs(reinterpret_cast<const float4*>(Hs + (size_t)gz * ld + gx2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        while (!mbar_try(bar + k, (par >> k) & 1u)) {}
+        par ^= 1u << k;
         // ---- 7T: receiver cotangents into the staged rectangle (duplicates legal -> shared atomics)
         if (inject) {
             for (int dz = -1; dz <= 1; ++dz) {
@@ -347,28 +472,23 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
             __syncthreads();
         }
         // ---- phase 1: lambda_p after undoing W and U (5T, 4T), 3T, and m = -alpha1*lambda_p ------------
-        if (p1_active) {
-            const int gz0 = Z0 + r01, gx0 = X0 + c01;
-            const ptrdiff_t cpo = (ptrdiff_t)gz0 * cpld + gx0;
+        if (R.p1_active) {
             float4 qw[RB + 3];     // (-alpha2w * lambda_w) rows r01-2 .. r01+5
 #pragma unroll
-            for (int k = 0; k < RB + 3; ++k) {
-                const float4 lw = ld4(lws + so1 + (k - 2) * RX);
-                const float4 aw = ldg4(a.cp.a2w + cpo + (ptrdiff_t)(k - 2) * cpld);
-                qw[k].x = (-aw.x) * lw.x; qw[k].y = (-aw.y) * lw.y; qw[k].z = (-aw.z) * lw.z; qw[k].w = (-aw.w) * lw.w;
+            for (int q = 0; q < RB + 3; ++q) {
+                const float4 lw = ld4(lws + R.so1 + (q - 2) * RX);
+                qw[q].x = NAW[q].x * lw.x; qw[q].y = NAW[q].y * lw.y; qw[q].z = NAW[q].z * lw.z; qw[q].w = NAW[q].w * lw.w;
             }
             float4 acc[RB];
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
-                const float* ur = lus + so1 + j * RX;
-                const float* ar = a.cp.a2u + cpo + (ptrdiff_t)j * cpld;
+                const float* ur = lus + R.so1 + j * RX;
                 const float2 ul = ld2(ur - 2); const float4 um = ld4(ur); const float uR = ur[4];
-                const float2 al = ldg2(ar - 2); const float4 am = ldg4(ar); const float aR = __ldg(ar + 4);
                 // qu at columns c0-2 .. c0+4
-                const float q0 = (-al.x) * ul.x, q1 = (-al.y) * ul.y, q2_ = (-am.x) * um.x, q3 = (-am.y) * um.y,
-                            q4 = (-am.z) * um.z, q5 = (-am.w) * um.w, q6 = (-aR) * uR;
+                const float q0 = NAU[j][0] * ul.x, q1 = NAU[j][1] * ul.y, q2_ = NAU[j][2] * um.x, q3 = NAU[j][3] * um.y,
+                            q4 = NAU[j][4] * um.z, q5 = NAU[j][5] * um.w, q6 = NAU[j][6] * uR;
                 const float4 w1 = qw[j + 1], w2 = qw[j + 2], w0 = qw[j], w3 = qw[j + 3];
-                float4 v = ld4(lps + so1 + j * RX);
+                float4 v = ld4(lps + R.so1 + j * RX);
                 // transposes of D+z and D+x:  +c1 m[z-1] - c1 m[z] + c2 m[z-2] - c2 m[z+1]
                 v.x += c1 * w1.x - c1 * w2.x + c2 * w0.x - c2 * w3.x;
                 v.y += c1 * w1.y - c1 * w2.y + c2 * w0.y - c2 * w3.y;
@@ -380,71 +500,108 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
                 v.w += c1 * q4 - c1 * q5 + c2 * q3 - c2 * q6;
                 acc[j] = v;
             }
-            if (FS && tzi == 0 && b1 == 0) {   // 3T: lambda_p[fs+1] -= lambda_p[fs-1]; lambda_p[fs-1] = 0 (block rows 3 and 1)
+            if (FS && tzi == 0 && R.b1 == 0) {   // 3T: lambda_p[fs+1] -= lambda_p[fs-1]; lambda_p[fs-1] = 0 (block rows 3 and 1)
                 acc[3].x -= acc[1].x; acc[3].y -= acc[1].y; acc[3].z -= acc[1].z; acc[3].w -= acc[1].w;
                 acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
-                const float4 a1 = ldg4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld);
                 float4 m;
-                m.x = (-a1.x) * acc[j].x; m.y = (-a1.y) * acc[j].y; m.z = (-a1.z) * acc[j].z; m.w = (-a1.w) * acc[j].w;
-                st4(lp1 + so1 + j * RX, acc[j]);
-                st4(mps + so1 + j * RX, m);
+                m.x = NA1[j].x * acc[j].x; m.y = NA1[j].y * acc[j].y; m.z = NA1[j].z * acc[j].z; m.w = NA1[j].w * acc[j].w;
+                st4(lp1 + R.so1 + j * RX, acc[j]);
+                st4(mps + R.so1 + j * RX, m);
             }
         }
         __syncthreads();
         // ---- phase 2: new lambda_u, lambda_w, lambda_p on the interior (5T,4T,1T), g_alpha1, g_src ---
         {
-            const int gx0 = X0 + c02, gz0 = Z0 + r02;
-            const bool colok = gx0 < ld;
-            const ptrdiff_t cpo = (ptrdiff_t)gz0 * cpld + gx0;
-            const float* Hs = a.hist + ((size_t)s * a.hist_len + a.tl) * g.plane;
             float4 M[7];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) M[k] = ld4(mps + so2 + (k - 1) * RX);
+            for (int q = 0; q < 7; ++q) M[q] = ld4(mps + R.so2 + (q - 1) * RX);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int gz = gz0 + j;
-                if (colok && gz < g.nzp) {
-                    const float* mr = mps + so2 + j * RX;
-                    const float mL = mr[-1];
-                    const float2 mR = ld2(mr + 4);
-                    const float4 m0 = M[j + 1], mm1 = M[j], mp1 = M[j + 2], mp2 = M[j + 3];
-                    const float4 qp = ld4(lp1 + so2 + j * RX);
-                    const float4 luo = ld4(lus + so2 + j * RX), lwo = ld4(lws + so2 + j * RX);
-                    const float4 k1 = ldg4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld), k2 = ldg4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld),
-                                 k3 = ldg4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld);
-                    const size_t cg = (size_t)gz * ld + gx0;
-                    const size_t o = (size_t)s * g.plane + cg;
-                    const float4 S = __ldcs(reinterpret_cast<const float4*>(Hs + cg));
-                    float4 nu, nw, np;
-                    // lambda_u: transpose of D-x:  +c1 m[x] - c1 m[x+1] + c2 m[x-1] - c2 m[x+2]
-                    nu.x = (1.0f - k2.x) * luo.x + (c1 * m0.x - c1 * m0.y + c2 * mL - c2 * m0.z);
-                    nu.y = (1.0f - k2.y) * luo.y + (c1 * m0.y - c1 * m0.z + c2 * m0.x - c2 * m0.w);
-                    nu.z = (1.0f - k2.z) * luo.z + (c1 * m0.z - c1 * m0.w + c2 * m0.y - c2 * mR.x);
-                    nu.w = (1.0f - k2.w) * luo.w + (c1 * m0.w - c1 * mR.x + c2 * m0.z - c2 * mR.y);
-                    // lambda_w: transpose of D-z:  +c1 m[z] - c1 m[z+1] + c2 m[z-1] - c2 m[z+2]
-                    nw.x = (1.0f - k3.x) * lwo.x + (c1 * m0.x - c1 * mp1.x + c2 * mm1.x - c2 * mp2.x);
-                    nw.y = (1.0f - k3.y) * lwo.y + (c1 * m0.y - c1 * mp1.y + c2 * mm1.y - c2 * mp2.y);
-                    nw.z = (1.0f - k3.z) * lwo.z + (c1 * m0.z - c1 * mp1.z + c2 * mm1.z - c2 * mp2.z);
-                    nw.w = (1.0f - k3.w) * lwo.w + (c1 * m0.w - c1 * mp1.w + c2 * mm1.w - c2 * mp2.w);
-                    np.x = (1.0f - k1.x) * qp.x; np.y = (1.0f - k1.y) * qp.y; np.z = (1.0f - k1.z) * qp.z; np.w = (1.0f - k1.w) * qp.w;
+                const int gz = gz2 + j;
+                const float* mr = mps + R.so2 + j * RX;
+                const float mL = mr[-1];
+                const float2 mR = ld2(mr + 4);
+                const float4 m0 = M[j + 1], mm1 = M[j], mp1 = M[j + 2], mp2 = M[j + 3];
+                const float4 qp = ld4(lp1 + R.so2 + j * RX);
+                const float4 luo = ld4(lus + R.so2 + j * RX), lwo = ld4(lws + R.so2 + j * RX);
+                float4 du, dw, nu, nw, np;
+                // lambda_u: transpose of D-x:  +c1 m[x] - c1 m[x+1] + c2 m[x-1] - c2 m[x+2]
+                du.x = c1 * m0.x - c1 * m0.y + c2 * mL - c2 * m0.z;
+                du.y = c1 * m0.y - c1 * m0.z + c2 * m0.x - c2 * m0.w;
+                du.z = c1 * m0.z - c1 * m0.w + c2 * m0.y - c2 * mR.x;
+                du.w = c1 * m0.w - c1 * mR.x + c2 * m0.z - c2 * mR.y;
+                // lambda_w: transpose of D-z:  +c1 m[z] - c1 m[z+1] + c2 m[z-1] - c2 m[z+2]
+                dw.x = c1 * m0.x - c1 * mp1.x + c2 * mm1.x - c2 * mp2.x;
+                dw.y = c1 * m0.y - c1 * mp1.y + c2 * mm1.y - c2 * mp2.y;
+                dw.z = c1 * m0.z - c1 * mp1.z + c2 * mm1.z - c2 * mp2.z;
+                dw.w = c1 * m0.w - c1 * mp1.w + c2 * mm1.w - c2 * mp2.w;
+                if (PML) {
+                    nu.x = T2[j].x * luo.x + du.x; nu.y = T2[j].y * luo.y + du.y; nu.z = T2[j].z * luo.z + du.z; nu.w = T2[j].w * luo.w + du.w;
+                    nw.x = T3[j].x * lwo.x + dw.x; nw.y = T3[j].y * lwo.y + dw.y; nw.z = T3[j].z * lwo.z + dw.z; nw.w = T3[j].w * lwo.w + dw.w;
+                    np.x = T1[j].x * qp.x; np.y = T1[j].y * qp.y; np.z = T1[j].z * qp.z; np.w = T1[j].w * qp.w;
+                } else {
+                    nu.x = luo.x + du.x; nu.y = luo.y + du.y; nu.z = luo.z + du.z; nu.w = luo.w + du.w;
+                    nw.x = lwo.x + dw.x; nw.y = lwo.y + dw.y; nw.z = lwo.z + dw.z; nw.w = lwo.w + dw.w;
+                    np = qp;
+                }
+                if (col2ok && gz < g.nzp) {
+                    const size_t o = (size_t)s * g.plane + (size_t)gz * ld + gx2;
                     st4(a.lu_out + o, nu);
                     st4(a.lw_out + o, nw);
                     st4(a.lp_out + o, np);
-                    float* gp1 = a.g1part + (size_t)sl * g.plane + cg;     // masked to the P region when reduced
-                    float4 ga = ld4(gp1);
-                    ga.x = ga.x - qp.x * S.x; ga.y = ga.y - qp.y * S.y; ga.z = ga.z - qp.z * S.z; ga.w = ga.w - qp.w * S.w;
-                    st4(gp1, ga);
                     if (a.g_src) {
-                        const int dz = (int)a.sz[s] - gz, dx = (int)a.sx[s] - gx0;
+                        const int dz = s_sz[s - s_lo] - gz, dx = s_sx[s - s_lo] - gx2;
                         if (dz == 0 && dx >= 0 && dx < 4)
                             a.g_src[(size_t)s * g.nt + a.it] = g.dt * (dx == 0 ? qp.x : dx == 1 ? qp.y : dx == 2 ? qp.z : qp.w);
                     }
                 }
+                // g_alpha1 -= lambda_p1 * S  (masked to the P region when reduced)
+                gacc[j].x = gacc[j].x - qp.x * Sh[j].x; gacc[j].y = gacc[j].y - qp.y * Sh[j].y;
+                gacc[j].z = gacc[j].z - qp.z * Sh[j].z; gacc[j].w = gacc[j].w - qp.w * Sh[j].w;
             }
         }
+        if (inject || (FS && tzi == 0)) fence_proxy_async();   // generic-proxy writes to the stage precede its TMA refill
+        __syncthreads();
+        if (tid == 0 && s + 2 < s_hi) {
+            float* st = (float*)(smem_raw + k * STAGE_BYTES);
+            fence_proxy_async();
+            mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
+            tma_load_3d(st, tm_lp, X0 - HX, Z0 - HZ, s + 2, bar + k);
+            tma_load_3d(st + RECT_BYTES / 4, tm_lu, X0 - HX, Z0 - HZ, s + 2, bar + k);
+            tma_load_3d(st + 2 * RECT_BYTES / 4, tm_lw, X0 - HX, Z0 - HZ, s + 2, bar + k);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int gz = gz2 + j;
+        if (col2ok && gz < g.nzp) red4(a.g1part + (size_t)chunk * g.plane + (size_t)gz * ld + gx2, gacc[j]);
+    }
+}
+
+template <bool FS>
+__global__ void __launch_bounds__(NTHREADS, 2)
+ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ CUtensorMap tm_lu,
+             const __grid_constant__ CUtensorMap tm_lw, const FGeom g, const AdjArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = (uint64_t*)(smem_raw + 2 * STAGE_BYTES + 2 * RECT_BYTES);
+    int* s_sz = (int*)(bar + 2);
+    int* s_sx = s_sz + CMAX;
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    const int nitems = g.ntx * g.ntz * a.nchunks;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
+        const int s_lo = a.s_begin + chunk * a.chunk;
+        const int s_hi = min(s_lo + a.chunk, a.s_end);
+        if (a.tflags[tile]) adj_tile<FS, true>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
+        else                adj_tile<FS, false>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
         __syncthreads();
     }
 }
@@ -472,6 +629,25 @@ __global__ void acf_pack_coefs(int nzp, int nxp, int fs, int cprows, int cpld, s
     pack[3 * cpplane + o] = inU ? k2[c] : 0.f;
     pack[4 * cpplane + o] = inW ? a2[c] : 0.f;
     pack[5 * cpplane + o] = inW ? k3[c] : 0.f;
+}
+
+// tile flag = 1 when the tile's neighbourhood (everything either kernel reads from the pack) has a
+// non-zero damping term or the U / W masks differ; 0 selects the variant without the kappa terms.
+__global__ void acf_tile_flags(const FGeom g, size_t cpplane, const float* __restrict__ pack, unsigned char* __restrict__ flags)
+{
+    const int tile = blockIdx.x;
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
+    const int W = TX + 2 * CPX, H = TZ + 2 * CPZ;
+    int bad = 0;
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
+        const int zz = Z0 + i / W, xx = X0 + i % W;            // pack coordinates (apron included)
+        const size_t o = (size_t)zz * g.cpld + xx;
+        if (pack[1 * cpplane + o] != 0.f || pack[3 * cpplane + o] != 0.f || pack[5 * cpplane + o] != 0.f) bad = 1;
+        if (pack[2 * cpplane + o] != pack[4 * cpplane + o]) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flags[tile] = (unsigned char)(bad ? 1 : 0);
 }
 
 // receiver buckets: counting sort of the receivers by tile
@@ -556,12 +732,25 @@ __global__ void acf_illum_finalize(int nzp, int nxp, int ld, int nabc, int npart
     if (ow) ow[o] = p + (u + iw[c]);
 }
 
+constexpr int FWD_SMEM = 2 * STAGE_BYTES + RECT_BYTES + 16 + 3 * CMAX * 4 + 64;
+constexpr int ADJ_SMEM = 2 * STAGE_BYTES + 2 * RECT_BYTES + 16 + 2 * CMAX * 4 + 64;
+constexpr int CTAS_PER_SM = 2;
+
+int acf_num_sms()
+{
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
 struct FPlan {
     FGeom g;
     int ns, nr, FS, save, n_segments;
     int K, nseg, nckpt, G;
+    int chunk, nchunks;             // shots one CTA walks through per tile; chunks per full group
     int cprows; size_t cpplane;
     float* pack;                    // 6 masked coefficient planes
+    unsigned char* tflags;
     float *st[2][3];                // p,u,w ping-pong
     float *lam[2][3];               // lambda ping-pong
     float *hist, *ckpt, *g1part, *ill_p, *ill_u, *ill_w;
@@ -569,7 +758,7 @@ struct FPlan {
     size_t bytes;
 };
 
-int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P)
+int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
 {
     FGeom& g = P->g;
     g.nzp = d->nzp; g.nxp = d->nxp; g.ld = (d->nxp + 31) / 32 * 32; g.nabc = d->nabc; g.nt = d->nt;
@@ -587,20 +776,25 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P)
     int K = d->ckpt_interval;
     if (K <= 0 || K >= d->nt) K = d->nt;
     P->K = K; P->nseg = cdiv(d->nt, K); P->nckpt = P->nseg > 2 ? P->nseg - 2 : 0;
+    // shots per launch: all of them by default (the wavefields stream through HBM; the tile-persistent
+    // CTAs amortise their coefficient loads over the shots they walk through)
     int G = d->shots_per_group;
-    if (G <= 0) {
-        const size_t per_shot = g.plane * sizeof(float) * 6;     // two buffers of three fields
-        G = (int)((size_t)(72u << 20) / per_shot);
-        if (G < 1) G = 1;
-    }
-    if (G > d->ns) G = d->ns;
+    if (G <= 0 || G > d->ns) G = d->ns;
     P->G = G;
+    // shots per CTA walk: enough (tile, chunk) items for ~3 rounds over the resident CTAs
+    const int ntiles = g.ntx * g.ntz;
+    int nchunks = d->reserved[1] > 0 ? cdiv(G, d->reserved[1]) : (3 * CTAS_PER_SM * nsm + ntiles / 2) / ntiles;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > G) nchunks = G;
+    int chunk = cdiv(G, nchunks);
+    if (chunk > CMAX) chunk = CMAX;
+    P->chunk = chunk; P->nchunks = cdiv(G, chunk);
     Carver cv(ws);
     const size_t sp = (size_t)d->ns * g.plane;
-    const int ntiles = g.ntx * g.ntz;
     P->pack = cv.take<float>(6 * P->cpplane);
+    P->tflags = cv.take<unsigned char>(ntiles);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->st[b][f] = cv.take<float>(sp);
-    P->ill_p = cv.take<float>((size_t)G * g.plane); P->ill_u = cv.take<float>((size_t)G * g.plane); P->ill_w = cv.take<float>(g.plane);
+    P->ill_p = cv.take<float>((size_t)P->nchunks * g.plane); P->ill_u = cv.take<float>((size_t)P->nchunks * g.plane); P->ill_w = cv.take<float>(g.plane);
     P->rcv_cnt = cv.take<int>(ntiles + 1); P->rcv_start = cv.take<int>(ntiles + 1); P->rcv_cursor = cv.take<int>(ntiles + 1);
     P->rcv_id = cv.take<int>(d->nr > 0 ? d->nr : 1); P->rcv_zx = cv.take<int>(d->nr > 0 ? d->nr : 1);
     P->rcv_nbr = cv.take<unsigned char>(ntiles);
@@ -608,23 +802,12 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P)
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->lam[b][f] = nullptr;
     if (P->save) {
         for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->lam[b][f] = cv.take<float>(sp);
-        P->g1part = cv.take<float>((size_t)G * g.plane);
+        P->g1part = cv.take<float>((size_t)P->nchunks * g.plane);
         if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * 3 * sp);
         P->hist = cv.take<float>((size_t)K * sp);
     }
     P->bytes = cv.off;
     return ADFWI_OK;
-}
-
-constexpr int FWD_SMEM = 4 * RECT_BYTES + 64;
-constexpr int ADJ_SMEM = 5 * RECT_BYTES + 64;
-constexpr int FWD_CTAS_PER_SM = 5, ADJ_CTAS_PER_SM = 4;
-
-int acf_num_sms()
-{
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-    return n;
 }
 
 template <typename K> int acf_set_smem(K kern, int bytes)
@@ -648,7 +831,8 @@ RcvBuckets acf_bucket_ptrs(const FPlan& P)
     return b;
 }
 
-// per-call set-up left in the workspace for the matching backward call: coefficient pack + buckets
+// per-call set-up left in the workspace for the matching backward call: coefficient pack, tile
+// flags, receiver buckets
 int acf_setup(const FPlan& P, cudaStream_t st, const float* const* coef, const int64_t* rx, const int64_t* rz)
 {
     const FGeom& g = P.g;
@@ -656,6 +840,8 @@ int acf_setup(const FPlan& P, cudaStream_t st, const float* const* coef, const i
                                                                       coef[0], coef[1], coef[2], coef[3], coef[4], P.pack);
     ADFWI_LAUNCH_CHECK();
     const int ntiles = g.ntx * g.ntz;
+    acf_tile_flags<<<ntiles, 128, 0, st>>>(g, P.cpplane, P.pack, P.tflags);
+    ADFWI_LAUNCH_CHECK();
     ADFWI_CUDA(cudaMemsetAsync(P.rcv_cnt, 0, sizeof(int) * (ntiles + 1), st));
     if (P.nr > 0) {
         acf_rcv_count<<<cdiv(P.nr, 128), 128, 0, st>>>(g, P.nr, rx, rz, P.rcv_cnt);
@@ -686,6 +872,14 @@ int acf_make_maps(const FPlan& P, StepMaps* M)
     return 0;
 }
 
+inline int acf_grid(const FPlan& P, int nshots, int* nchunks)
+{
+    *nchunks = cdiv(nshots, P.chunk);
+    const int nitems = P.g.ntx * P.g.ntz * *nchunks;
+    const int cap = CTAS_PER_SM * acf_num_sms();
+    return nitems < cap ? nitems : cap;
+}
+
 // one fused forward step of shots [sb,se): reads buffer cur, writes buffer cur^1
 int acf_forward_step(const FPlan& P, const StepMaps& M, cudaStream_t st, int cur, int sb, int se, int it, bool save, int tl,
                      const float* src_v, const int64_t* sx, const int64_t* sz,
@@ -693,17 +887,15 @@ int acf_forward_step(const FPlan& P, const StepMaps& M, cudaStream_t st, int cur
 {
     const FGeom& g = P.g;
     FwdArgs a;
-    a.cp = acf_pack_ptrs(P);
+    a.cp = acf_pack_ptrs(P); a.tflags = P.tflags;
     a.p_out = P.st[cur ^ 1][0]; a.u_out = P.st[cur ^ 1][1]; a.w_out = P.st[cur ^ 1][2];
     a.src_v = src_v; a.sx = sx; a.sz = sz;
     a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it;
     a.nr = rcv_p ? P.nr : 0; a.rb = acf_bucket_ptrs(P);
     a.rcv_p = rcv_p; a.rcv_u = rcv_u; a.rcv_w = rcv_w;
     a.ill_p = P.ill_p; a.ill_u = P.ill_u; a.acc_u = acc_u;
-    a.s_begin = sb; a.s_end = se;
-    const int nitems = g.ntx * g.ntz * (se - sb);
-    const int cap = FWD_CTAS_PER_SM * acf_num_sms();
-    const int grid = nitems < cap ? nitems : cap;
+    a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
+    const int grid = acf_grid(P, se - sb, &a.nchunks);
     TimedLaunch tl_(KC_AC_FWD_FUSED, st);
 #define LF(FSv, SVv, ILv) ac_fwd_fused<FSv, SVv, ILv><<<grid, NTHREADS, FWD_SMEM, st>>>(M.st[cur][0], M.st[cur][1], M.st[cur][2], g, a)
     if (P.FS) { if (save) { if (illum) LF(true, true, true); else LF(true, true, false); } else { if (illum) LF(true, false, true); else LF(true, false, false); } }
@@ -732,14 +924,14 @@ int acf_init_kernels()
 size_t acf_workspace_bytes(const adfwi_acoustic_desc* d)
 {
     FPlan P;
-    acf_make_plan(d, nullptr, &P);
+    acf_make_plan(d, nullptr, &P, 148);     // workspace size must not depend on the device queried
     return P.bytes;
 }
 
 int acf_group_size(const adfwi_acoustic_desc* d)
 {
     FPlan P;
-    acf_make_plan(d, nullptr, &P);
+    acf_make_plan(d, nullptr, &P, 148);
     return P.G;
 }
 
@@ -748,7 +940,7 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
                 float* illum_p, float* illum_u, float* illum_w, void* ws, cudaStream_t st)
 {
     FPlan P;
-    acf_make_plan(d, ws, &P);
+    acf_make_plan(d, ws, &P, 148);
     const FGeom& g = P.g;
     if (g.nzp >= 32768 || g.nxp >= 65536) return ADFWI_E_DIMS;      // receiver cells are packed as (z<<16)|x
     int rc = acf_init_kernels();
@@ -763,8 +955,8 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
     const int csz = cdiv(nt, P.n_segments);
     const int last_chunk_start = (cdiv(nt, csz) - 1) * csz;
     if (illum) {
-        ADFWI_CUDA(cudaMemsetAsync(P.ill_p, 0, sizeof(float) * (size_t)P.G * g.plane, st));
-        ADFWI_CUDA(cudaMemsetAsync(P.ill_u, 0, sizeof(float) * (size_t)P.G * g.plane, st));
+        ADFWI_CUDA(cudaMemsetAsync(P.ill_p, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
+        ADFWI_CUDA(cudaMemsetAsync(P.ill_u, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
         ADFWI_CUDA(cudaMemsetAsync(P.ill_w, 0, sizeof(float) * g.plane, st));
     }
     for (int sb = 0; sb < P.ns; sb += P.G) {
@@ -792,7 +984,7 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
     }
     if (illum) {
         const int nx = g.nxp - 2 * g.nabc, nz = g.nzp - 2 * g.nabc;
-        acf_illum_finalize<<<dim3(cdiv(nx, 128), nz), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.nabc, P.G, g.plane, P.ill_p, P.ill_u, P.ill_w,
+        acf_illum_finalize<<<dim3(cdiv(nx, 128), nz), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.nabc, P.nchunks, g.plane, P.ill_p, P.ill_u, P.ill_w,
                                                                      illum_p, illum_u, illum_w);
         ADFWI_LAUNCH_CHECK();
     }
@@ -805,24 +997,21 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
 {
     (void)coef; (void)rx; (void)rz;
     FPlan P;
-    acf_make_plan(d, ws, &P);
+    acf_make_plan(d, ws, &P, 148);
     const FGeom& g = P.g;
     int rc = acf_init_kernels();
     if (rc) return rc;
     StepMaps M;
     rc = acf_make_maps(P, &M);
     if (rc) return rc;
-    // the coefficient pack and the receiver buckets were left in the workspace by the forward call
+    // the coefficient pack, tile flags and receiver buckets were left in the workspace by the forward call
     const int nt = g.nt;
-    ADFWI_CUDA(cudaMemsetAsync(P.g1part, 0, sizeof(float) * (size_t)P.G * g.plane, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.g1part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
         const size_t off = (size_t)sb * g.plane, cnt = (size_t)(se - sb) * g.plane * sizeof(float);
         for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) ADFWI_CUDA(cudaMemsetAsync(P.lam[b][f] + off, 0, cnt, st));
         int lcur = 0;
-        const int nitems = g.ntx * g.ntz * (se - sb);
-        const int cap = ADJ_CTAS_PER_SM * acf_num_sms();
-        const int grid = nitems < cap ? nitems : cap;
         for (int seg = P.nseg - 1; seg >= 0; --seg) {
             const int t0 = seg * P.K, t1 = t0 + P.K < nt ? t0 + P.K : nt;
             if (seg != P.nseg - 1) {
@@ -842,11 +1031,12 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
             }
             for (int it = t1 - 1; it >= t0; --it) {
                 AdjArgs a;
-                a.cp = acf_pack_ptrs(P);
+                a.cp = acf_pack_ptrs(P); a.tflags = P.tflags;
                 a.lp_out = P.lam[lcur ^ 1][0]; a.lu_out = P.lam[lcur ^ 1][1]; a.lw_out = P.lam[lcur ^ 1][2];
                 a.sx = sx; a.sz = sz; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it;
                 a.nr = P.nr; a.rb = acf_bucket_ptrs(P); a.gp = gp; a.gu = gu; a.gw = gw;
-                a.g1part = P.g1part; a.g_src = g_src; a.s_begin = sb; a.s_end = se;
+                a.g1part = P.g1part; a.g_src = g_src; a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
+                const int grid = acf_grid(P, se - sb, &a.nchunks);
                 {
                     TimedLaunch tl_(KC_AC_ADJ_FUSED, st);
                     if (P.FS) ac_adj_fused<true><<<grid, NTHREADS, ADJ_SMEM, st>>>(M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a);
@@ -857,7 +1047,7 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
             }
         }
     }
-    acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.G, P.g1part, g_alpha1);
+    acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g1part, g_alpha1);
     ADFWI_LAUNCH_CHECK();
     return ADFWI_OK;
 }

@@ -26,8 +26,10 @@ config = {
     "ckpt_interval": int(os.environ["ADFWI_B200_CKPT_INTERVAL"]) if "ADFWI_B200_CKPT_INTERVAL" in os.environ else None,
     # fraction of the currently free device memory the workspace may take
     "memory_fraction": float(os.environ.get("ADFWI_B200_MEM_FRACTION", "0.85")),
-    # shots advanced together inside the library (0 = library picks for L2 residency)
+    # shots advanced per kernel launch inside the library (0 = all shots of the call)
     "shots_per_group": int(os.environ.get("ADFWI_B200_SHOTS_PER_GROUP", "0")),
+    # shots one CTA of the fused kernels walks through per tile (0 = library picks)
+    "shots_per_chunk": int(os.environ.get("ADFWI_B200_SHOTS_PER_CHUNK", "0")),
     # True: run the generic one-cell-per-thread kernels instead of the fused TMA pipeline
     # (cross-checks in the tests; the density gradient always uses the generic kernels)
     "force_generic": os.environ.get("ADFWI_B200_GENERIC", "0") == "1",
@@ -99,6 +101,7 @@ class AcousticFD(torch.autograd.Function):
         desc = make_desc(nzp, nxp, ns, nt, nr, nabc, free_surface, dt, n_segments, save,
                          0, need[1], config["shots_per_group"])
         desc.reserved[0] = 1 if config["force_generic"] else 0
+        desc.reserved[1] = int(config.get("shots_per_chunk", 0))
         with torch.cuda.device(dev):
             if save:
                 if config["ckpt_interval"] is not None:

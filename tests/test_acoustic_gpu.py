@@ -72,7 +72,8 @@ def _run_vp_only(g, comp, **cfg):
 
 @pytest.mark.parametrize("name", ["acoustic_fs", "acoustic_nofs"])
 @pytest.mark.parametrize("cfg", [dict(), dict(ckpt_interval=40, shots_per_group=1), dict(ckpt_interval=64),
-                                 dict(force_generic=True)])
+                                 dict(force_generic=True), dict(shots_per_chunk=2), dict(shots_per_chunk=3, shots_per_group=3),
+                                 dict(shots_per_chunk=8, ckpt_interval=50)])
 def test_fused_pipeline_vp_only(golden_dir, name, cfg):
     """vp-only gradients take the fused TMA pipeline (the default fast path); force_generic
     cross-checks the generic kernels on the same inputs."""
@@ -93,18 +94,18 @@ def test_fused_large_grid_matches_generic():
     from adfwi_b200.propagator import acoustic_kernels as ak
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    nz, nx, nabc, nt, ns = 83, 149, 12, 120, 3
+    nz, nx, nabc, nt, ns = 83, 149, 12, 120, 5
     v = (1800 + 1500 * torch.rand(nz, nx, device=dev))
     rho = 2000 + 200 * torch.rand(nz, nx, device=dev)
     damp = 30 * torch.rand(nz + 2 * nabc, nx + 2 * nabc, device=dev)
-    sx = torch.tensor([3, 70, 140], device=dev); sz = torch.tensor([0, 40, 2], device=dev)
+    sx = torch.tensor([3, 70, 140, 64, 63], device=dev); sz = torch.tensor([0, 40, 2, 31, 32], device=dev)
     rx = torch.arange(0, nx, 2, device=dev); rz = torch.cat([torch.zeros(40, dtype=torch.long), torch.full((35,), 50)]).to(dev)
     src = torch.randn(ns, nt, device=dev)
     W = torch.randn(ns, nt, rx.numel(), device=dev)
     out = {}
     for fs in (True, False):
         for mode in (False, True):
-            old = dict(ak.config); ak.config.update(force_generic=mode, shots_per_group=2)
+            old = dict(ak.config); ak.config.update(force_generic=mode, shots_per_group=(2 if mode else 0), shots_per_chunk=(5 if fs else 2))
             try:
                 vv = v.clone().requires_grad_(True)
                 rec = ak.forward_kernel(nx, nz, 10.0, 10.0, nt, 1e-3, nabc, fs, sx, sz, ns, src, rx, rz, rx.numel(), damp, vv, rho, device=dev)
