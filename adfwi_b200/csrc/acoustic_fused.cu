@@ -55,6 +55,7 @@ static_assert(RX <= NTHREADS && CMAX <= NTHREADS, "row fix-ups / scalar staging 
 constexpr int RECT_BYTES = ((RZ * RX * 4 + 127) / 128) * 128;   // 11008
 constexpr int STAGE_BYTES = 3 * RECT_BYTES;                      // p,u,w of one shot
 constexpr int CPX = 8, CPZ = 4;             // apron of the coefficient pack (cells)
+constexpr int TSM_BYTES = 12 * NTHREADS * 16;                    // adjoint: (1-kappa) factors parked in shared memory
 
 struct FGeom {
     int nzp, nxp, ld, fs, zlo, nabc, nt;
@@ -102,8 +103,63 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// coefficient-pack loads: read-only path, kept in L2 (evict_last) while the wavefields stream through
+__device__ __forceinline__ uint64_t l2_keep_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldk4(const float* p, uint64_t pol)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ldk2(const float* p, uint64_t pol)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ldk1(const float* p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// (tile, shot) sequence of one persistent CTA: items blockIdx.x, +gridDim.x, ...; each item is one
+// tile and one chunk of the group's shots.  The TMA producer runs two shots ahead of the compute
+// along this flat sequence, across tile boundaries.
+struct Cursor {
+    int item, s, s_hi, X0, Z0; bool valid;
+    __device__ __forceinline__ void set(int it, const FGeom& g, int s_begin, int s_end, int chunk, int nchunks)
+    {
+        item = it; valid = it < g.ntx * g.ntz * nchunks;
+        if (valid) {
+            const int tile = it / nchunks, ch = it - tile * nchunks;
+            const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+            X0 = txi * TX; Z0 = g.zlo + tzi * TZ;
+            s = s_begin + ch * chunk; s_hi = min(s + chunk, s_end);
+        }
+    }
+    __device__ __forceinline__ void next(const FGeom& g, int s_begin, int s_end, int chunk, int nchunks)
+    {
+        if (valid && ++s >= s_hi) set(item + gridDim.x, g, s_begin, s_end, chunk, nchunks);
+    }
+};
+__device__ __forceinline__ void issue_stage(const Cursor& c, unsigned char* smem_raw, uint64_t* bar, int k,
+                                            const CUtensorMap* t0, const CUtensorMap* t1, const CUtensorMap* t2)
+{
+    float* st = (float*)(smem_raw + k * STAGE_BYTES);
+    fence_proxy_async();
+    mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
+    tma_load_3d(st, t0, c.X0 - HX, c.Z0 - HZ, c.s, bar + k);
+    tma_load_3d(st + RECT_BYTES / 4, t1, c.X0 - HX, c.Z0 - HZ, c.s, bar + k);
+    tma_load_3d(st + 2 * RECT_BYTES / 4, t2, c.X0 - HX, c.Z0 - HZ, c.s, bar + k);
+}
+
 __device__ __forceinline__ void red4(float* p, const float4& v)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -129,27 +185,16 @@ struct Roles {
 template <bool FS, bool SAVE, bool ILLUM, bool PML>
 __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensorMap* tm_u, const CUtensorMap* tm_w,
                                          const FGeom& g, const FwdArgs& a, unsigned char* smem_raw, uint64_t* bar,
-                                         uint32_t& par, int* s_sz, int* s_sx, float* s_sv,
+                                         uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx, float* s_sv,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk)
 {
     float* pn = (float*)(smem_raw + 2 * STAGE_BYTES);
+    const uint64_t pol = l2_keep_policy();
     const int ld = g.ld, cpld = g.cpld;
     const float c1 = g.c1, c2 = g.c2;
     const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
     const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
-    // ---- prologue: start the first two shots' loads, stage per-shot scalars, load coefficients -----
-    if (tid == 0) {
-        fence_proxy_async();
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (s_lo + k < s_hi) {
-                float* st = (float*)(smem_raw + k * STAGE_BYTES);
-                mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
-                tma_load_3d(st, tm_p, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
-                tma_load_3d(st + RECT_BYTES / 4, tm_u, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
-                tma_load_3d(st + 2 * RECT_BYTES / 4, tm_w, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
-            }
-    }
+    // ---- prologue: stage per-shot scalars, load this tile's coefficients into registers ----------
     if (tid < s_hi - s_lo) {
         const int s = s_lo + tid;
         s_sz[tid] = (int)a.sz[s]; s_sx[tid] = (int)a.sx[s];
@@ -162,8 +207,8 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
         const ptrdiff_t cpo = (ptrdiff_t)gz1 * cpld + gx1;       // may be negative: the pack has an apron
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
-            A1[j] = ldg4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld);
-            if (PML) T1[j] = one_minus(ldg4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld));
+            A1[j] = ldk4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld, pol);
+            if (PML) T1[j] = one_minus(ldk4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld, pol));
         }
     }
     float4 AU[4], AW[4], T2[4], T3[4];
@@ -171,11 +216,11 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
         const ptrdiff_t cpo = (ptrdiff_t)gz2 * cpld + gx2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            AU[j] = ldg4(a.cp.a2u + cpo + (ptrdiff_t)j * cpld);
+            AU[j] = ldk4(a.cp.a2u + cpo + (ptrdiff_t)j * cpld, pol);
             if (PML) {
-                AW[j] = ldg4(a.cp.a2w + cpo + (ptrdiff_t)j * cpld);
-                T2[j] = one_minus(ldg4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld));
-                T3[j] = one_minus(ldg4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld));
+                AW[j] = ldk4(a.cp.a2w + cpo + (ptrdiff_t)j * cpld, pol);
+                T2[j] = one_minus(ldk4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld, pol));
+                T3[j] = one_minus(ldk4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld, pol));
             }
         }
     }
@@ -189,7 +234,7 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
     __syncthreads();          // s_sz/s_sx/s_sv visible
 
     for (int s = s_lo; s < s_hi; ++s) {
-        const int k = (s - s_lo) & 1;
+        const int k = stage;
         const float* ps = (const float*)(smem_raw + k * STAGE_BYTES);
         float* us = (float*)(smem_raw + k * STAGE_BYTES + RECT_BYTES);
         float* ws = (float*)(smem_raw + k * STAGE_BYTES + 2 * RECT_BYTES);
@@ -314,14 +359,9 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
             fence_proxy_async();      // generic-proxy writes to the stage precede its TMA refill
         }
         __syncthreads();
-        if (tid == 0 && s + 2 < s_hi) {       // refill this stage with shot s+2 while shot s+1 is computed
-            float* st = (float*)(smem_raw + k * STAGE_BYTES);
-            fence_proxy_async();
-            mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
-            tma_load_3d(st, tm_p, X0 - HX, Z0 - HZ, s + 2, bar + k);
-            tma_load_3d(st + RECT_BYTES / 4, tm_u, X0 - HX, Z0 - HZ, s + 2, bar + k);
-            tma_load_3d(st + 2 * RECT_BYTES / 4, tm_w, X0 - HX, Z0 - HZ, s + 2, bar + k);
-        }
+        // refill this stage with the (tile, shot) two steps ahead while the next one is computed
+        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_p, tm_u, tm_w); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+        stage ^= 1;
     }
     if (ILLUM) {
 #pragma unroll
@@ -351,13 +391,19 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     __syncthreads();
     const Roles R(tid);
     uint32_t par = 0;
+    int stage = 0;
     const int nitems = g.ntx * g.ntz * a.nchunks;
+    Cursor pc;
+    pc.set(blockIdx.x, g, a.s_begin, a.s_end, a.chunk, a.nchunks);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, &tm_p, &tm_u, &tm_w); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
-        if (a.tflags[tile]) fwd_tile<FS, SAVE, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
-        else                fwd_tile<FS, SAVE, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
+        if (a.tflags[tile]) fwd_tile<FS, SAVE, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
+        else                fwd_tile<FS, SAVE, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
         __syncthreads();      // per-shot scalars and stages are reused by the next item
     }
 }
@@ -368,28 +414,18 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 template <bool FS, bool PML>
 __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw,
                                          const FGeom& g, const AdjArgs& a, unsigned char* smem_raw, uint64_t* bar,
-                                         uint32_t& par, int* s_sz, int* s_sx,
+                                         uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk)
 {
     float* lp1 = (float*)(smem_raw + 2 * STAGE_BYTES);                  // lambda_p after undoing W,U (and 3T)
     float* mps = (float*)(smem_raw + 2 * STAGE_BYTES + RECT_BYTES);     // m = -alpha1 * lambda_p1
+    float4* tsm = (float4*)(smem_raw + 2 * STAGE_BYTES + 2 * RECT_BYTES);   // per-thread (1-kappa) factors, [12][NTHREADS]
+    const uint64_t pol = l2_keep_policy();
     const int ld = g.ld, cpld = g.cpld;
     const float c1 = g.c1, c2 = g.c2;
     const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
     const int X0 = txi * TX, Z0 = g.zlo + tzi * TZ;
     const bool have_g = a.nr > 0 && (a.gp || a.gu || a.gw);
-    if (tid == 0) {
-        fence_proxy_async();
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (s_lo + k < s_hi) {
-                float* st = (float*)(smem_raw + k * STAGE_BYTES);
-                mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
-                tma_load_3d(st, tm_lp, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
-                tma_load_3d(st + RECT_BYTES / 4, tm_lu, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
-                tma_load_3d(st + 2 * RECT_BYTES / 4, tm_lw, X0 - HX, Z0 - HZ, s_lo + k, bar + k);
-            }
-    }
     if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
     const int gz1 = Z0 + R.r01, gx1 = X0 + R.c01;
     const int gz2 = Z0 + R.r02, gx2 = X0 + R.c02;
@@ -400,23 +436,22 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
     if (R.p1_active) {
         const ptrdiff_t cpo = (ptrdiff_t)gz1 * cpld + gx1;
 #pragma unroll
-        for (int q = 0; q < RB + 3; ++q) NAW[q] = neg4(ldg4(a.cp.a2w + cpo + (ptrdiff_t)(q - 2) * cpld));
+        for (int q = 0; q < RB + 3; ++q) NAW[q] = neg4(ldk4(a.cp.a2w + cpo + (ptrdiff_t)(q - 2) * cpld, pol));
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             const float* ar = a.cp.a2u + cpo + (ptrdiff_t)j * cpld;
-            const float2 al = ldg2(ar - 2); const float4 am = ldg4(ar); const float aR = __ldg(ar + 4);
+            const float2 al = ldk2(ar - 2, pol); const float4 am = ldk4(ar, pol); const float aR = ldk1(ar + 4, pol);
             NAU[j][0] = -al.x; NAU[j][1] = -al.y; NAU[j][2] = -am.x; NAU[j][3] = -am.y; NAU[j][4] = -am.z; NAU[j][5] = -am.w; NAU[j][6] = -aR;
-            NA1[j] = neg4(ldg4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld));
+            NA1[j] = neg4(ldk4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld, pol));
         }
     }
-    float4 T1[4], T2[4], T3[4];
-    if (PML) {
+    if (PML) {       // (1-kappa) of the thread's phase-2 cells: parked in shared memory (register budget)
         const ptrdiff_t cpo = (ptrdiff_t)gz2 * cpld + gx2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            T1[j] = one_minus(ldg4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld));
-            T2[j] = one_minus(ldg4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld));
-            T3[j] = one_minus(ldg4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld));
+            tsm[(3 * j + 0) * NTHREADS + tid] = one_minus(ldk4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld, pol));
+            tsm[(3 * j + 1) * NTHREADS + tid] = one_minus(ldk4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld, pol));
+            tsm[(3 * j + 2) * NTHREADS + tid] = one_minus(ldk4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld, pol));
         }
     }
     float4 gacc[4];
@@ -427,7 +462,7 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
     __syncthreads();
 
     for (int s = s_lo; s < s_hi; ++s) {
-        const int k = (s - s_lo) & 1;
+        const int k = stage;
         float* lps = (float*)(smem_raw + k * STAGE_BYTES);
         float* lus = (float*)(smem_raw + k * STAGE_BYTES + RECT_BYTES);
         float* lws = (float*)(smem_raw + k * STAGE_BYTES + 2 * RECT_BYTES);
@@ -539,9 +574,10 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
                 dw.z = c1 * m0.z - c1 * mp1.z + c2 * mm1.z - c2 * mp2.z;
                 dw.w = c1 * m0.w - c1 * mp1.w + c2 * mm1.w - c2 * mp2.w;
                 if (PML) {
-                    nu.x = T2[j].x * luo.x + du.x; nu.y = T2[j].y * luo.y + du.y; nu.z = T2[j].z * luo.z + du.z; nu.w = T2[j].w * luo.w + du.w;
-                    nw.x = T3[j].x * lwo.x + dw.x; nw.y = T3[j].y * lwo.y + dw.y; nw.z = T3[j].z * lwo.z + dw.z; nw.w = T3[j].w * lwo.w + dw.w;
-                    np.x = T1[j].x * qp.x; np.y = T1[j].y * qp.y; np.z = T1[j].z * qp.z; np.w = T1[j].w * qp.w;
+                    const float4 t1 = tsm[(3 * j + 0) * NTHREADS + tid], t2 = tsm[(3 * j + 1) * NTHREADS + tid], t3 = tsm[(3 * j + 2) * NTHREADS + tid];
+                    nu.x = t2.x * luo.x + du.x; nu.y = t2.y * luo.y + du.y; nu.z = t2.z * luo.z + du.z; nu.w = t2.w * luo.w + du.w;
+                    nw.x = t3.x * lwo.x + dw.x; nw.y = t3.y * lwo.y + dw.y; nw.z = t3.z * lwo.z + dw.z; nw.w = t3.w * lwo.w + dw.w;
+                    np.x = t1.x * qp.x; np.y = t1.y * qp.y; np.z = t1.z * qp.z; np.w = t1.w * qp.w;
                 } else {
                     nu.x = luo.x + du.x; nu.y = luo.y + du.y; nu.z = luo.z + du.z; nu.w = luo.w + du.w;
                     nw.x = lwo.x + dw.x; nw.y = lwo.y + dw.y; nw.z = lwo.z + dw.z; nw.w = lwo.w + dw.w;
@@ -565,14 +601,8 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
         }
         if (inject || (FS && tzi == 0)) fence_proxy_async();   // generic-proxy writes to the stage precede its TMA refill
         __syncthreads();
-        if (tid == 0 && s + 2 < s_hi) {
-            float* st = (float*)(smem_raw + k * STAGE_BYTES);
-            fence_proxy_async();
-            mbar_expect_tx(bar + k, 3 * RZ * RX * 4);
-            tma_load_3d(st, tm_lp, X0 - HX, Z0 - HZ, s + 2, bar + k);
-            tma_load_3d(st + RECT_BYTES / 4, tm_lu, X0 - HX, Z0 - HZ, s + 2, bar + k);
-            tma_load_3d(st + 2 * RECT_BYTES / 4, tm_lw, X0 - HX, Z0 - HZ, s + 2, bar + k);
-        }
+        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+        stage ^= 1;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -587,7 +617,7 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
              const __grid_constant__ CUtensorMap tm_lw, const FGeom g, const AdjArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bar = (uint64_t*)(smem_raw + 2 * STAGE_BYTES + 2 * RECT_BYTES);
+    uint64_t* bar = (uint64_t*)(smem_raw + 2 * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES);
     int* s_sz = (int*)(bar + 2);
     int* s_sx = s_sz + CMAX;
     const int tid = threadIdx.x;
@@ -595,13 +625,19 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
     __syncthreads();
     const Roles R(tid);
     uint32_t par = 0;
+    int stage = 0;
     const int nitems = g.ntx * g.ntz * a.nchunks;
+    Cursor pc;
+    pc.set(blockIdx.x, g, a.s_begin, a.s_end, a.chunk, a.nchunks);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, &tm_lp, &tm_lu, &tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
-        if (a.tflags[tile]) adj_tile<FS, true>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
-        else                adj_tile<FS, false>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
+        if (a.tflags[tile]) adj_tile<FS, true>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
+        else                adj_tile<FS, false>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
         __syncthreads();
     }
 }
@@ -733,7 +769,7 @@ __global__ void acf_illum_finalize(int nzp, int nxp, int ld, int nabc, int npart
 }
 
 constexpr int FWD_SMEM = 2 * STAGE_BYTES + RECT_BYTES + 16 + 3 * CMAX * 4 + 64;
-constexpr int ADJ_SMEM = 2 * STAGE_BYTES + 2 * RECT_BYTES + 16 + 2 * CMAX * 4 + 64;
+constexpr int ADJ_SMEM = 2 * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES + 16 + 2 * CMAX * 4 + 64;
 constexpr int CTAS_PER_SM = 2;
 
 int acf_num_sms()
