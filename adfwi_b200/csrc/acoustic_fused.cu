@@ -34,6 +34,7 @@
 #ifndef ADFWI_HOST_EMUL
 #include "tma.cuh"
 #include "acoustic_fused.h"
+#include <stdlib.h>
 
 namespace adfwi {
 
@@ -66,7 +67,7 @@ struct FGeom {
 };
 
 // coefficient pack: masked planes, pointers pre-offset to logical cell (0,0)
-struct CoefPack { const float *a1, *k1, *a2u, *k2, *a2w, *k3; };
+struct CoefPack { const float *a1, *k1, *a2u, *k2, *a2w, *k3, *ew; };   // ew: adjoint scale of the w cotangent (see adj_tile)
 
 struct RcvBuckets { const int* start; const int* id; const int* zx; const unsigned char* nbr; };
 
@@ -116,18 +117,6 @@ __device__ __forceinline__ float4 ldk4(const float* p, uint64_t pol)
     asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ float2 ldk2(const float* p, uint64_t pol)
-{
-    float2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ldk1(const float* p, uint64_t pol)
-{
-    float v;
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
 
 // (tile, shot) sequence of one persistent CTA: items blockIdx.x, +gridDim.x, ...; each item is one
 // tile and one chunk of the group's shots.  The TMA producer runs two shots ahead of the compute
@@ -160,6 +149,12 @@ __device__ __forceinline__ void issue_stage(const Cursor& c, unsigned char* smem
     tma_load_3d(st + 2 * RECT_BYTES / 4, t2, c.X0 - HX, c.Z0 - HZ, c.s, bar + k);
 }
 
+// programmatic dependent launch: the next time step's grid may become resident while this one drains
+// (its prologue -- barrier init, coefficient loads -- overlaps our tail); it must not touch anything we
+// produce before griddep_wait() returns, i.e. before this grid has completed and flushed.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void red4(float* p, const float4& v)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -186,7 +181,7 @@ template <bool FS, bool SAVE, bool ILLUM, bool PML>
 __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensorMap* tm_u, const CUtensorMap* tm_w,
                                          const FGeom& g, const FwdArgs& a, unsigned char* smem_raw, uint64_t* bar,
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx, float* s_sv,
-                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk)
+                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
 {
     float* pn = (float*)(smem_raw + 2 * STAGE_BYTES);
     const uint64_t pol = l2_keep_policy();
@@ -231,6 +226,13 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
     const bool has_rcv = rcv_hi > rcv_lo;
     const bool col1ok = (R.gi1 >= 0) && (R.gi1 < NG) && (gx1 < ld);
     const bool col2ok = gx2 < ld;
+    if (first) {      // first tile of this CTA: the coefficient loads above are in flight; now wait for the previous
+                      // step's grid and start the TMA producer (two stages ahead)
+        griddep_wait();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_p, tm_u, tm_w); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+    }
     __syncthreads();          // s_sz/s_sx/s_sv visible
 
     for (int s = s_lo; s < s_hi; ++s) {
@@ -395,27 +397,33 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     const int nitems = g.ntx * g.ntz * a.nchunks;
     Cursor pc;
     pc.set(blockIdx.x, g, a.s_begin, a.s_end, a.chunk, a.nchunks);
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, &tm_p, &tm_u, &tm_w); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+    griddep_launch_dependents();
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
-        if (a.tflags[tile]) fwd_tile<FS, SAVE, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
-        else                fwd_tile<FS, SAVE, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk);
+        const bool first = item == (int)blockIdx.x;
+        if (a.tflags[tile]) fwd_tile<FS, SAVE, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk, first);
+        else                fwd_tile<FS, SAVE, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk, first);
         __syncthreads();      // per-shot scalars and stages are reused by the next item
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // adjoint: one tile, shots [s_lo, s_hi)
+//
+// State carried between reverse steps: lambda_p and the SCALED velocity cotangents
+//     mu_u = alpha2u * lambda_u,   mu_w = ew * lambda_w      (ew = alpha2w on the W region; 1 on row fs-1
+//                                                            with a free surface, where lambda_w is parked raw)
+// alpha2 is time-invariant, so mu obeys  mu_new = (1-kappa)*mu + alpha2 * D^T(m): the coefficient is needed
+// only at the thread's own cells (phase 2) and phase 1 -- lambda_p1 = lambda_p + D+z^T(-mu_w) + D+x^T(-mu_u)
+// -- needs no coefficient at all.  Cells outside a region have alpha2 = 0 there and never feed back.
 // ------------------------------------------------------------------------------------------
 template <bool FS, bool PML>
 __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw,
                                          const FGeom& g, const AdjArgs& a, unsigned char* smem_raw, uint64_t* bar,
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx,
-                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk)
+                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
 {
     float* lp1 = (float*)(smem_raw + 2 * STAGE_BYTES);                  // lambda_p after undoing W,U (and 3T)
     float* mps = (float*)(smem_raw + 2 * STAGE_BYTES + RECT_BYTES);     // m = -alpha1 * lambda_p1
@@ -429,29 +437,24 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
     if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
     const int gz1 = Z0 + R.r01, gx1 = X0 + R.c01;
     const int gz2 = Z0 + R.r02, gx2 = X0 + R.c02;
-    // phase-1 coefficients: -alpha2w rows r01-2..r01+5 (own columns), -alpha2u columns c01-2..c01+4 of
-    // the five rows, -alpha1 of the five rows
-    float4 NAW[RB + 3], NA1[RB];
-    float NAU[RB][7];
+    float4 NA1[RB];
     if (R.p1_active) {
         const ptrdiff_t cpo = (ptrdiff_t)gz1 * cpld + gx1;
 #pragma unroll
-        for (int q = 0; q < RB + 3; ++q) NAW[q] = neg4(ldk4(a.cp.a2w + cpo + (ptrdiff_t)(q - 2) * cpld, pol));
-#pragma unroll
-        for (int j = 0; j < RB; ++j) {
-            const float* ar = a.cp.a2u + cpo + (ptrdiff_t)j * cpld;
-            const float2 al = ldk2(ar - 2, pol); const float4 am = ldk4(ar, pol); const float aR = ldk1(ar + 4, pol);
-            NAU[j][0] = -al.x; NAU[j][1] = -al.y; NAU[j][2] = -am.x; NAU[j][3] = -am.y; NAU[j][4] = -am.z; NAU[j][5] = -am.w; NAU[j][6] = -aR;
-            NA1[j] = neg4(ldk4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld, pol));
-        }
+        for (int j = 0; j < RB; ++j) NA1[j] = neg4(ldk4(a.cp.a1 + cpo + (ptrdiff_t)j * cpld, pol));
     }
-    if (PML) {       // (1-kappa) of the thread's phase-2 cells: parked in shared memory (register budget)
+    float4 EU[4], EW[4];
+    {
         const ptrdiff_t cpo = (ptrdiff_t)gz2 * cpld + gx2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            tsm[(3 * j + 0) * NTHREADS + tid] = one_minus(ldk4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld, pol));
-            tsm[(3 * j + 1) * NTHREADS + tid] = one_minus(ldk4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld, pol));
-            tsm[(3 * j + 2) * NTHREADS + tid] = one_minus(ldk4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld, pol));
+            EU[j] = ldk4(a.cp.a2u + cpo + (ptrdiff_t)j * cpld, pol);
+            if (PML) {       // (1-kappa) of the thread's phase-2 cells: parked in shared memory (register budget)
+                EW[j] = ldk4(a.cp.ew + cpo + (ptrdiff_t)j * cpld, pol);
+                tsm[(3 * j + 0) * NTHREADS + tid] = one_minus(ldk4(a.cp.k1 + cpo + (ptrdiff_t)j * cpld, pol));
+                tsm[(3 * j + 1) * NTHREADS + tid] = one_minus(ldk4(a.cp.k2 + cpo + (ptrdiff_t)j * cpld, pol));
+                tsm[(3 * j + 2) * NTHREADS + tid] = one_minus(ldk4(a.cp.k3 + cpo + (ptrdiff_t)j * cpld, pol));
+            }
         }
     }
     float4 gacc[4];
@@ -459,6 +462,12 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
     for (int j = 0; j < 4; ++j) gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool inject = have_g && a.rb.nbr[tile];
     const bool col2ok = gx2 < ld;
+    if (first) {
+        griddep_wait();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+    }
     __syncthreads();
 
     for (int s = s_lo; s < s_hi; ++s) {
@@ -478,7 +487,8 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
         }
         while (!mbar_try(bar + k, (par >> k) & 1u)) {}
         par ^= 1u << k;
-        // ---- 7T: receiver cotangents into the staged rectangle (duplicates legal -> shared atomics)
+        // ---- 7T: receiver cotangents into the staged rectangle (duplicates legal -> shared atomics);
+        //      the u / w cotangents enter scaled by the cell's alpha2 (mu = alpha2 * lambda)
         if (inject) {
             for (int dz = -1; dz <= 1; ++dz) {
                 const int tz2 = tzi + dz;
@@ -490,49 +500,51 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
                     const int lo = a.rb.start[t2], hi = a.rb.start[t2 + 1];
                     for (int i = lo + tid; i < hi; i += NTHREADS) {
                         const int zx = a.rb.zx[i];
-                        const int z = (zx >> 16) - (Z0 - HZ), x = (zx & 0xffff) - (X0 - HX);
+                        const int rz = zx >> 16, rx = zx & 0xffff;
+                        const int z = rz - (Z0 - HZ), x = rx - (X0 - HX);
                         if (z >= 0 && z < RZ && x >= 0 && x < RX) {
                             const size_t o = ((size_t)s * g.nt + a.it) * a.nr + a.rb.id[i];
+                            const ptrdiff_t co = (ptrdiff_t)rz * cpld + rx;
                             if (a.gp) atomicAdd(lps + z * RX + x, a.gp[o]);
-                            if (a.gu) atomicAdd(lus + z * RX + x, a.gu[o]);
-                            if (a.gw) atomicAdd(lws + z * RX + x, a.gw[o]);
+                            if (a.gu) atomicAdd(lus + z * RX + x, a.cp.a2u[co] * a.gu[o]);
+                            if (a.gw) atomicAdd(lws + z * RX + x, a.cp.ew[co] * a.gw[o]);
                         }
                     }
                 }
             }
             __syncthreads();
         }
-        if (FS && tzi == 0) {        // 6T: lambda_w[fs] += lambda_w[fs-1]; lambda_w[fs-1] = 0  (staged rows HZ+1 and HZ)
-            if (tid < RX) { lws[(HZ + 1) * RX + tid] += lws[HZ * RX + tid]; lws[HZ * RX + tid] = 0.f; }
+        if (FS && tzi == 0) {        // 6T: lambda_w[fs] += lambda_w[fs-1]; lambda_w[fs-1] = 0  (staged rows HZ+1 and HZ;
+                                     //     row fs-1 holds the raw cotangent, row fs the scaled one)
+            if (tid < RX) {
+                const float e = a.cp.a2w[(ptrdiff_t)(Z0 + 1) * cpld + (X0 - HX + tid)];
+                lws[(HZ + 1) * RX + tid] += e * lws[HZ * RX + tid]; lws[HZ * RX + tid] = 0.f;
+            }
             __syncthreads();
         }
         // ---- phase 1: lambda_p after undoing W and U (5T, 4T), 3T, and m = -alpha1*lambda_p ------------
         if (R.p1_active) {
-            float4 qw[RB + 3];     // (-alpha2w * lambda_w) rows r01-2 .. r01+5
+            float4 qw[RB + 3];     // mu_w rows r01-2 .. r01+5
 #pragma unroll
-            for (int q = 0; q < RB + 3; ++q) {
-                const float4 lw = ld4(lws + R.so1 + (q - 2) * RX);
-                qw[q].x = NAW[q].x * lw.x; qw[q].y = NAW[q].y * lw.y; qw[q].z = NAW[q].z * lw.z; qw[q].w = NAW[q].w * lw.w;
-            }
+            for (int q = 0; q < RB + 3; ++q) qw[q] = ld4(lws + R.so1 + (q - 2) * RX);
             float4 acc[RB];
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 const float* ur = lus + R.so1 + j * RX;
                 const float2 ul = ld2(ur - 2); const float4 um = ld4(ur); const float uR = ur[4];
-                // qu at columns c0-2 .. c0+4
-                const float q0 = NAU[j][0] * ul.x, q1 = NAU[j][1] * ul.y, q2_ = NAU[j][2] * um.x, q3 = NAU[j][3] * um.y,
-                            q4 = NAU[j][4] * um.z, q5 = NAU[j][5] * um.w, q6 = NAU[j][6] * uR;
+                // mu_u at columns c0-2 .. c0+4
+                const float q0 = ul.x, q1 = ul.y, q2_ = um.x, q3 = um.y, q4 = um.z, q5 = um.w, q6 = uR;
                 const float4 w1 = qw[j + 1], w2 = qw[j + 2], w0 = qw[j], w3 = qw[j + 3];
                 float4 v = ld4(lps + R.so1 + j * RX);
-                // transposes of D+z and D+x:  +c1 m[z-1] - c1 m[z] + c2 m[z-2] - c2 m[z+1]
-                v.x += c1 * w1.x - c1 * w2.x + c2 * w0.x - c2 * w3.x;
-                v.y += c1 * w1.y - c1 * w2.y + c2 * w0.y - c2 * w3.y;
-                v.z += c1 * w1.z - c1 * w2.z + c2 * w0.z - c2 * w3.z;
-                v.w += c1 * w1.w - c1 * w2.w + c2 * w0.w - c2 * w3.w;
-                v.x += c1 * q1 - c1 * q2_ + c2 * q0 - c2 * q3;
-                v.y += c1 * q2_ - c1 * q3 + c2 * q1 - c2 * q4;
-                v.z += c1 * q3 - c1 * q4 + c2 * q2_ - c2 * q5;
-                v.w += c1 * q4 - c1 * q5 + c2 * q3 - c2 * q6;
+                // transposes of D+z and D+x applied to -mu:  -c1 mu[z-1] + c1 mu[z] - c2 mu[z-2] + c2 mu[z+1]
+                v.x += c1 * w2.x - c1 * w1.x + c2 * w3.x - c2 * w0.x;
+                v.y += c1 * w2.y - c1 * w1.y + c2 * w3.y - c2 * w0.y;
+                v.z += c1 * w2.z - c1 * w1.z + c2 * w3.z - c2 * w0.z;
+                v.w += c1 * w2.w - c1 * w1.w + c2 * w3.w - c2 * w0.w;
+                v.x += c1 * q2_ - c1 * q1 + c2 * q3 - c2 * q0;
+                v.y += c1 * q3 - c1 * q2_ + c2 * q4 - c2 * q1;
+                v.z += c1 * q4 - c1 * q3 + c2 * q5 - c2 * q2_;
+                v.w += c1 * q5 - c1 * q4 + c2 * q6 - c2 * q3;
                 acc[j] = v;
             }
             if (FS && tzi == 0 && R.b1 == 0) {   // 3T: lambda_p[fs+1] -= lambda_p[fs-1]; lambda_p[fs-1] = 0 (block rows 3 and 1)
@@ -548,7 +560,7 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
             }
         }
         __syncthreads();
-        // ---- phase 2: new lambda_u, lambda_w, lambda_p on the interior (5T,4T,1T), g_alpha1, g_src ---
+        // ---- phase 2: new mu_u, mu_w, lambda_p on the interior (5T,4T,1T), g_alpha1, g_src ------------
         {
             float4 M[7];
 #pragma unroll
@@ -562,17 +574,18 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
                 const float4 m0 = M[j + 1], mm1 = M[j], mp1 = M[j + 2], mp2 = M[j + 3];
                 const float4 qp = ld4(lp1 + R.so2 + j * RX);
                 const float4 luo = ld4(lus + R.so2 + j * RX), lwo = ld4(lws + R.so2 + j * RX);
+                const float4 eu = EU[j], ew = PML ? EW[j] : EU[j];
                 float4 du, dw, nu, nw, np;
-                // lambda_u: transpose of D-x:  +c1 m[x] - c1 m[x+1] + c2 m[x-1] - c2 m[x+2]
-                du.x = c1 * m0.x - c1 * m0.y + c2 * mL - c2 * m0.z;
-                du.y = c1 * m0.y - c1 * m0.z + c2 * m0.x - c2 * m0.w;
-                du.z = c1 * m0.z - c1 * m0.w + c2 * m0.y - c2 * mR.x;
-                du.w = c1 * m0.w - c1 * mR.x + c2 * m0.z - c2 * mR.y;
-                // lambda_w: transpose of D-z:  +c1 m[z] - c1 m[z+1] + c2 m[z-1] - c2 m[z+2]
-                dw.x = c1 * m0.x - c1 * mp1.x + c2 * mm1.x - c2 * mp2.x;
-                dw.y = c1 * m0.y - c1 * mp1.y + c2 * mm1.y - c2 * mp2.y;
-                dw.z = c1 * m0.z - c1 * mp1.z + c2 * mm1.z - c2 * mp2.z;
-                dw.w = c1 * m0.w - c1 * mp1.w + c2 * mm1.w - c2 * mp2.w;
+                // transpose of D-x:  +c1 m[x] - c1 m[x+1] + c2 m[x-1] - c2 m[x+2]
+                du.x = eu.x * (c1 * m0.x - c1 * m0.y + c2 * mL - c2 * m0.z);
+                du.y = eu.y * (c1 * m0.y - c1 * m0.z + c2 * m0.x - c2 * m0.w);
+                du.z = eu.z * (c1 * m0.z - c1 * m0.w + c2 * m0.y - c2 * mR.x);
+                du.w = eu.w * (c1 * m0.w - c1 * mR.x + c2 * m0.z - c2 * mR.y);
+                // transpose of D-z:  +c1 m[z] - c1 m[z+1] + c2 m[z-1] - c2 m[z+2]
+                dw.x = ew.x * (c1 * m0.x - c1 * mp1.x + c2 * mm1.x - c2 * mp2.x);
+                dw.y = ew.y * (c1 * m0.y - c1 * mp1.y + c2 * mm1.y - c2 * mp2.y);
+                dw.z = ew.z * (c1 * m0.z - c1 * mp1.z + c2 * mm1.z - c2 * mp2.z);
+                dw.w = ew.w * (c1 * m0.w - c1 * mp1.w + c2 * mm1.w - c2 * mp2.w);
                 if (PML) {
                     const float4 t1 = tsm[(3 * j + 0) * NTHREADS + tid], t2 = tsm[(3 * j + 1) * NTHREADS + tid], t3 = tsm[(3 * j + 2) * NTHREADS + tid];
                     nu.x = t2.x * luo.x + du.x; nu.y = t2.y * luo.y + du.y; nu.z = t2.z * luo.z + du.z; nu.w = t2.w * luo.w + du.w;
@@ -629,24 +642,23 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
     const int nitems = g.ntx * g.ntz * a.nchunks;
     Cursor pc;
     pc.set(blockIdx.x, g, a.s_begin, a.s_end, a.chunk, a.nchunks);
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, &tm_lp, &tm_lu, &tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+    griddep_launch_dependents();
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
-        if (a.tflags[tile]) adj_tile<FS, true>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
-        else                adj_tile<FS, false>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk);
+        const bool first = item == (int)blockIdx.x;
+        if (a.tflags[tile]) adj_tile<FS, true>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
+        else                adj_tile<FS, false>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
         __syncthreads();
     }
 }
 
 // ---- set-up kernels ------------------------------------------------------------------------------
-// coefficient pack: six planes [cprows][cpld], logical cell (z,x) at [(z+CPZ)*cpld + x+CPX]; each
+// coefficient pack: seven planes [cprows][cpld], logical cell (z,x) at [(z+CPZ)*cpld + x+CPX]; each
 // plane is the caller's coefficient inside the update region of the field it drives and 0 elsewhere
 // (update regions: SURVEY.md Appendix A.1 / acoustic_kernels.py:115,139,151).
-__global__ void acf_pack_coefs(int nzp, int nxp, int fs, int cprows, int cpld, size_t cpplane,
+__global__ void acf_pack_coefs(int nzp, int nxp, int fs, int free_surface, int cprows, int cpld, size_t cpplane,
                                const float* __restrict__ a1, const float* __restrict__ k1, const float* __restrict__ a2,
                                const float* __restrict__ k2, const float* __restrict__ k3, float* __restrict__ pack)
 {
@@ -665,6 +677,8 @@ __global__ void acf_pack_coefs(int nzp, int nxp, int fs, int cprows, int cpld, s
     pack[3 * cpplane + o] = inU ? k2[c] : 0.f;
     pack[4 * cpplane + o] = inW ? a2[c] : 0.f;
     pack[5 * cpplane + o] = inW ? k3[c] : 0.f;
+    // adjoint scale of the w cotangent: alpha2 on the W region, 1 on the free-surface row fs-1
+    pack[6 * cpplane + o] = inW ? a2[c] : ((free_surface && in && z == fs - 1) ? 1.0f : 0.f);
 }
 
 // tile flag = 1 when the tile's neighbourhood (everything either kernel reads from the pack) has a
@@ -680,7 +694,7 @@ __global__ void acf_tile_flags(const FGeom g, size_t cpplane, const float* __res
         const int zz = Z0 + i / W, xx = X0 + i % W;            // pack coordinates (apron included)
         const size_t o = (size_t)zz * g.cpld + xx;
         if (pack[1 * cpplane + o] != 0.f || pack[3 * cpplane + o] != 0.f || pack[5 * cpplane + o] != 0.f) bad = 1;
-        if (pack[2 * cpplane + o] != pack[4 * cpplane + o]) bad = 1;
+        if (pack[2 * cpplane + o] != pack[4 * cpplane + o] || pack[2 * cpplane + o] != pack[6 * cpplane + o]) bad = 1;
     }
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) flags[tile] = (unsigned char)(bad ? 1 : 0);
@@ -785,7 +799,7 @@ struct FPlan {
     int K, nseg, nckpt, G;
     int chunk, nchunks;             // shots one CTA walks through per tile; chunks per full group
     int cprows; size_t cpplane;
-    float* pack;                    // 6 masked coefficient planes
+    float* pack;                    // 7 masked coefficient planes
     unsigned char* tflags;
     float *st[2][3];                // p,u,w ping-pong
     float *lam[2][3];               // lambda ping-pong
@@ -827,7 +841,7 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
     P->chunk = chunk; P->nchunks = cdiv(G, chunk);
     Carver cv(ws);
     const size_t sp = (size_t)d->ns * g.plane;
-    P->pack = cv.take<float>(6 * P->cpplane);
+    P->pack = cv.take<float>(7 * P->cpplane);
     P->tflags = cv.take<unsigned char>(ntiles);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->st[b][f] = cv.take<float>(sp);
     P->ill_p = cv.take<float>((size_t)P->nchunks * g.plane); P->ill_u = cv.take<float>((size_t)P->nchunks * g.plane); P->ill_w = cv.take<float>(g.plane);
@@ -858,6 +872,7 @@ CoefPack acf_pack_ptrs(const FPlan& P)
     c.a1 = P.pack + 0 * P.cpplane + o; c.k1 = P.pack + 1 * P.cpplane + o;
     c.a2u = P.pack + 2 * P.cpplane + o; c.k2 = P.pack + 3 * P.cpplane + o;
     c.a2w = P.pack + 4 * P.cpplane + o; c.k3 = P.pack + 5 * P.cpplane + o;
+    c.ew = P.pack + 6 * P.cpplane + o;
     return c;
 }
 
@@ -872,7 +887,7 @@ RcvBuckets acf_bucket_ptrs(const FPlan& P)
 int acf_setup(const FPlan& P, cudaStream_t st, const float* const* coef, const int64_t* rx, const int64_t* rz)
 {
     const FGeom& g = P.g;
-    acf_pack_coefs<<<dim3(cdiv(g.cpld, 128), P.cprows), 128, 0, st>>>(g.nzp, g.nxp, g.fs, P.cprows, g.cpld, P.cpplane,
+    acf_pack_coefs<<<dim3(cdiv(g.cpld, 128), P.cprows), 128, 0, st>>>(g.nzp, g.nxp, g.fs, P.FS, P.cprows, g.cpld, P.cpplane,
                                                                       coef[0], coef[1], coef[2], coef[3], coef[4], P.pack);
     ADFWI_LAUNCH_CHECK();
     const int ntiles = g.ntx * g.ntz;
@@ -895,6 +910,25 @@ int acf_setup(const FPlan& P, cudaStream_t st, const float* const* coef, const i
 }
 
 struct StepMaps { CUtensorMap st[2][3]; CUtensorMap lam[2][3]; };
+
+// launch with the programmatic-stream-serialization attribute (PDL): see griddep_wait() in the kernels
+template <typename Kern, typename... Args>
+cudaError_t acf_launch(Kern kern, int grid, int smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+inline bool acf_use_pdl()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 
 int acf_make_maps(const FPlan& P, StepMaps* M)
 {
@@ -933,7 +967,7 @@ int acf_forward_step(const FPlan& P, const StepMaps& M, cudaStream_t st, int cur
     a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
     const int grid = acf_grid(P, se - sb, &a.nchunks);
     TimedLaunch tl_(KC_AC_FWD_FUSED, st);
-#define LF(FSv, SVv, ILv) ac_fwd_fused<FSv, SVv, ILv><<<grid, NTHREADS, FWD_SMEM, st>>>(M.st[cur][0], M.st[cur][1], M.st[cur][2], g, a)
+#define LF(FSv, SVv, ILv) ADFWI_CUDA(acf_launch(ac_fwd_fused<FSv, SVv, ILv>, grid, FWD_SMEM, st, acf_use_pdl(), M.st[cur][0], M.st[cur][1], M.st[cur][2], g, a))
     if (P.FS) { if (save) { if (illum) LF(true, true, true); else LF(true, true, false); } else { if (illum) LF(true, false, true); else LF(true, false, false); } }
     else      { if (save) { if (illum) LF(false, true, true); else LF(false, true, false); } else { if (illum) LF(false, false, true); else LF(false, false, false); } }
 #undef LF
@@ -1075,8 +1109,8 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
                 const int grid = acf_grid(P, se - sb, &a.nchunks);
                 {
                     TimedLaunch tl_(KC_AC_ADJ_FUSED, st);
-                    if (P.FS) ac_adj_fused<true><<<grid, NTHREADS, ADJ_SMEM, st>>>(M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a);
-                    else      ac_adj_fused<false><<<grid, NTHREADS, ADJ_SMEM, st>>>(M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a);
+                    if (P.FS) ADFWI_CUDA(acf_launch(ac_adj_fused<true>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a));
+                    else      ADFWI_CUDA(acf_launch(ac_adj_fused<false>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a));
                 }
                 ADFWI_LAUNCH_CHECK();
                 lcur ^= 1;
