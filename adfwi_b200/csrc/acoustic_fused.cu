@@ -56,6 +56,7 @@ static_assert(RX <= NTHREADS && CMAX <= NTHREADS, "row fix-ups / scalar staging 
 constexpr int RECT_BYTES = ((RZ * RX * 4 + 127) / 128) * 128;   // 11008
 constexpr int STAGE_BYTES = 3 * RECT_BYTES;                      // p,u,w of one shot
 constexpr int CPX = 8, CPZ = 4;             // apron of the coefficient pack (cells)
+constexpr int FWD_STAGES = 2, ADJ_STAGES = 2;                     // TMA pipeline depth (shots in flight + 1)
 constexpr int TSM_BYTES = 12 * NTHREADS * 16;                    // adjoint: (1-kappa) factors parked in shared memory
 
 struct FGeom {
@@ -183,7 +184,7 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx, float* s_sv,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
 {
-    float* pn = (float*)(smem_raw + 2 * STAGE_BYTES);
+    float* pn = (float*)(smem_raw + FWD_STAGES * STAGE_BYTES);
     const uint64_t pol = l2_keep_policy();
     const int ld = g.ld, cpld = g.cpld;
     const float c1 = g.c1, c2 = g.c2;
@@ -230,7 +231,7 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
                       // step's grid and start the TMA producer (two stages ahead)
         griddep_wait();
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < FWD_STAGES; ++k)
             if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_p, tm_u, tm_w); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
     }
     __syncthreads();          // s_sz/s_sx/s_sv visible
@@ -363,7 +364,7 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
         __syncthreads();
         // refill this stage with the (tile, shot) two steps ahead while the next one is computed
         if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_p, tm_u, tm_w); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
-        stage ^= 1;
+        stage = (stage + 1 == FWD_STAGES) ? 0 : stage + 1;
     }
     if (ILLUM) {
 #pragma unroll
@@ -384,12 +385,12 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tm_w, const FGeom g, const FwdArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bar = (uint64_t*)(smem_raw + 2 * STAGE_BYTES + RECT_BYTES);
-    int* s_sz = (int*)(bar + 2);
+    uint64_t* bar = (uint64_t*)(smem_raw + FWD_STAGES * STAGE_BYTES + RECT_BYTES);
+    int* s_sz = (int*)(bar + 4);
     int* s_sx = s_sz + CMAX;
     float* s_sv = (float*)(s_sx + CMAX);
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    if (tid == 0) { for (int k = 0; k < FWD_STAGES; ++k) mbar_init(bar + k, 1); }
     __syncthreads();
     const Roles R(tid);
     uint32_t par = 0;
@@ -425,9 +426,9 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
 {
-    float* lp1 = (float*)(smem_raw + 2 * STAGE_BYTES);                  // lambda_p after undoing W,U (and 3T)
-    float* mps = (float*)(smem_raw + 2 * STAGE_BYTES + RECT_BYTES);     // m = -alpha1 * lambda_p1
-    float4* tsm = (float4*)(smem_raw + 2 * STAGE_BYTES + 2 * RECT_BYTES);   // per-thread (1-kappa) factors, [12][NTHREADS]
+    float* lp1 = (float*)(smem_raw + ADJ_STAGES * STAGE_BYTES);                  // lambda_p after undoing W,U (and 3T)
+    float* mps = (float*)(smem_raw + ADJ_STAGES * STAGE_BYTES + RECT_BYTES);     // m = -alpha1 * lambda_p1
+    float4* tsm = (float4*)(smem_raw + ADJ_STAGES * STAGE_BYTES + 2 * RECT_BYTES);   // per-thread (1-kappa) factors, [12][NTHREADS]
     const uint64_t pol = l2_keep_policy();
     const int ld = g.ld, cpld = g.cpld;
     const float c1 = g.c1, c2 = g.c2;
@@ -465,7 +466,7 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
     if (first) {
         griddep_wait();
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < ADJ_STAGES; ++k)
             if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
     }
     __syncthreads();
@@ -615,7 +616,7 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
         if (inject || (FS && tzi == 0)) fence_proxy_async();   // generic-proxy writes to the stage precede its TMA refill
         __syncthreads();
         if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
-        stage ^= 1;
+        stage = (stage + 1 == ADJ_STAGES) ? 0 : stage + 1;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -630,11 +631,11 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
              const __grid_constant__ CUtensorMap tm_lw, const FGeom g, const AdjArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bar = (uint64_t*)(smem_raw + 2 * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES);
-    int* s_sz = (int*)(bar + 2);
+    uint64_t* bar = (uint64_t*)(smem_raw + ADJ_STAGES * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES);
+    int* s_sz = (int*)(bar + 4);
     int* s_sx = s_sz + CMAX;
     const int tid = threadIdx.x;
-    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    if (tid == 0) { for (int k = 0; k < ADJ_STAGES; ++k) mbar_init(bar + k, 1); }
     __syncthreads();
     const Roles R(tid);
     uint32_t par = 0;
@@ -782,8 +783,10 @@ __global__ void acf_illum_finalize(int nzp, int nxp, int ld, int nabc, int npart
     if (ow) ow[o] = p + (u + iw[c]);
 }
 
-constexpr int FWD_SMEM = 2 * STAGE_BYTES + RECT_BYTES + 16 + 3 * CMAX * 4 + 64;
-constexpr int ADJ_SMEM = 2 * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES + 16 + 2 * CMAX * 4 + 64;
+constexpr int FWD_SMEM = FWD_STAGES * STAGE_BYTES + RECT_BYTES + 32 + 3 * CMAX * 4 + 64;
+constexpr int ADJ_SMEM = ADJ_STAGES * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES + 32 + 2 * CMAX * 4 + 64;
+static_assert(FWD_STAGES <= 4 && ADJ_STAGES <= 4, "four mbarrier slots are reserved");
+static_assert(2 * (FWD_SMEM + 1024) <= 233472 && 2 * (ADJ_SMEM + 1024) <= 233472, "two CTAs per SM must fit in shared memory");
 constexpr int CTAS_PER_SM = 2;
 
 int acf_num_sms()

@@ -283,12 +283,24 @@ def run_b200(args, wl):
             d = make_desc(nzp, nxp, batch, nt, wl["nr"], nabc, True, dt, 1, True, 0, False, ak_config["shots_per_group"])
             G = lib.adfwi_acoustic_group_size(ctypes.byref(d))   # shots one launch advances
             G_cells = G * nzp * nxp
-            dom_name, dom_ms, dom_bytes = ("adjoint step (ac_adj_inject+ac_adj_a+ac_adj_b)", adj, B_ADJ) if adj >= fwd else \
-                                          ("forward step (ac_fwd_p+ac_fwd_uw+ac_record)", fwd, B_FWD_SAVE)
+            fused = "ac_adj_fused" in avg or "ac_fwd_fused" in avg
+            dom_name, dom_ms, dom_bytes, dom_key = \
+                (("adjoint step (ac_adj_fused)" if fused else "adjoint step (ac_adj_inject+ac_adj_a+ac_adj_b)"), adj, B_ADJ, "ac_adj_fused") if adj >= fwd else \
+                (("forward step, recording (ac_fwd_fused)" if fused else "forward step (ac_fwd_p+ac_fwd_uw+ac_record)"), fwd, B_FWD_SAVE, "ac_fwd_fused")
+            # measured DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this command
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):
+                try:
+                    tj = json.load(open(tpath))
+                    if tj.get("workload") == args.workload and tj.get("batch") == batch:
+                        traffic = tj.get(dom_key)
+                except Exception:
+                    traffic = None
             if dom_ms > 0:
                 ach = dom_bytes * G_cells / (dom_ms * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": None, "kernel": dom_name, "avg_launch_ms": dom_ms,
+                        "traffic": traffic, "kernel": dom_name, "avg_launch_ms": dom_ms,
                         "algorithmic_bytes_per_cell_update": dom_bytes, "cells_per_launch": G_cells,
                         "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                         "whole_step_frac": B_GRAD_STEP / 2 * value * 1e9 / world / (peak * 1e9),
