@@ -13,6 +13,7 @@
 //   el_adj_stress : own-cell transpose of the stress update -> g_C11..g_C55, scratch planes nA..nD
 //   el_adj_stress_g : gathers D^T(n) into lambda_vx, lambda_vz (pre-step)
 #include "common.cuh"
+#include "elastic_fused.h"
 
 namespace adfwi {
 
@@ -726,10 +727,25 @@ static int el_backward_t(const ElPlan& P, cudaStream_t st, const ElArgs& a, cons
 
 using namespace adfwi;
 
+// The TMA-staged pipeline (elastic_fused.cu) is the default for the split-field PML; the generic
+// kernels of this file run for the sponge (ABL) boundary or when the caller sets bit 0 of
+// desc->reserved[0] (used by the tests to cross-check the two pipelines).
+static bool el_use_fused(const adfwi_elastic_desc* d)
+{
+#ifdef ADFWI_HOST_EMUL
+    (void)d; return false;
+#else
+    return elf_supported(d);
+#endif
+}
+
 extern "C" size_t adfwi_elastic_workspace_bytes(const adfwi_elastic_desc* desc)
 {
     ElPlan P;
     if (el_make_plan(desc, nullptr, &P) != ADFWI_OK) return 0;
+#ifndef ADFWI_HOST_EMUL
+    if (el_use_fused(desc)) return elf_workspace_bytes(desc);
+#endif
     return P.bytes;
 }
 
@@ -758,10 +774,16 @@ extern "C" int adfwi_elastic_forward(const adfwi_elastic_desc* desc, const float
     int rc = el_make_plan(desc, workspace, &P);
     if (rc) return rc;
     ElArgs a;
-    rc = el_check_args(P, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, workspace, workspace_bytes, &a);
+    rc = el_check_args(P, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, workspace, el_use_fused(desc) ? (size_t)-1 : workspace_bytes, &a);
     if (rc) return rc;
     if (P.nr > 0) { if (!rcv) return ADFWI_E_NULL; for (int k = 0; k < 5; ++k) if (!rcv[k]) return ADFWI_E_NULL; }
     cudaStream_t st = (cudaStream_t)stream;
+#ifndef ADFWI_HOST_EMUL
+    if (el_use_fused(desc)) {
+        if (workspace_bytes < elf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
+        return elf_forward(desc, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, rcv, illum, workspace, st);
+    }
+#endif
     return EL_DISPATCH(el_forward_t, P, st, a, rcv, illum);
 }
 
@@ -777,10 +799,16 @@ extern "C" int adfwi_elastic_backward(const adfwi_elastic_desc* desc, const floa
     if (rc) return rc;
     if (!P.save) return ADFWI_E_MODE;
     ElArgs a;
-    rc = el_check_args(P, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, workspace, workspace_bytes, &a);
+    rc = el_check_args(P, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, workspace, el_use_fused(desc) ? (size_t)-1 : workspace_bytes, &a);
     if (rc) return rc;
     if (!g_rcv || !g_coef) return ADFWI_E_NULL;
     for (int k = 0; k < 6; ++k) if (!g_coef[k]) return ADFWI_E_NULL;
     cudaStream_t st = (cudaStream_t)stream;
+#ifndef ADFWI_HOST_EMUL
+    if (el_use_fused(desc)) {
+        if (workspace_bytes < elf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
+        return elf_backward(desc, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, g_rcv, g_coef, g_src_v, workspace, st);
+    }
+#endif
     return EL_DISPATCH(el_backward_t, P, st, a, g_rcv, g_coef, g_src_v);
 }

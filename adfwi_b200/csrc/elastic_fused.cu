@@ -1,0 +1,1590 @@
+// elastic_fused.cu -- TMA-staged, tile-persistent split-PML elastic time step for sm_100a (fast path).
+//
+// Semantics: ADFWI/propagator/elastic_kernels.py:339-418 (O(2,4)) / :495-575 (O(2,6)) and the
+// reverse-mode derivative of that loop; same arithmetic and association as
+// the generic kernels of elastic.cu (-fmad=false): forward records stay bit-identical to the CPU
+// reference.  Used for abc_type "PML"; the sponge (ABL) variants run the generic kernels.
+//
+// Two launches per forward step and two per reverse step, each a single stencil layer deep:
+//   elf_s  : stress update.  Reads the 4 velocity split fields with a halo (sums and the free-surface
+//            velocity rows are formed on chip), updates the 6 stress split fields IN PLACE (own cell
+//            only), writes the 3 stress sums and, in recording mode, the 4 velocity derivatives the
+//            adjoint needs (history; own cell, so the adjoint needs no halo and no recomputation).
+//   elf_v  : velocity update.  Reads the 3 stress sums with a halo (free-surface mirrors applied on
+//            chip), updates the 4 velocity split fields in place, samples the receivers, writes the 4
+//            stress derivatives of the history.
+//   elf_k1 : adjoint of the velocity update: record cotangents + free-surface transpose on chip,
+//            own-cell transpose on tile + ring (halo recompute), gather of the operator transposes
+//            into the stress-sum cotangents; g_bx, g_bz accumulate in registers.
+//   elf_k2 : adjoint of the stress update: same structure; g_C11, g_C13, g_C33, g_C55 in registers,
+//            gather into the velocity-sum cotangents; g_src.
+// Common skeleton (the one of acoustic_fused.cu): a CTA of 128 threads owns one 64(x) x 16(z) tile
+// and walks through a chunk of the launch's shots.  Coefficients, PML factors and gradient sums of
+// the thread's 8 cells stay in REGISTERS for the whole walk; per shot every field a kernel touches
+// is brought into shared memory by TMA (hardware zero fill outside the grid) into a double buffer,
+// the loads of shot s+1 in flight while shot s is computed; all shared-memory traffic is 128-bit.
+// Tiles whose neighbourhood has no damping run a variant without the PML factors (x*1 == x exactly).
+// Launches are chained with programmatic dependent launch.
+#include "common.cuh"
+#ifndef ADFWI_HOST_EMUL
+#include "tma.cuh"
+#include "elastic_fused.h"
+#include <stdlib.h>
+
+namespace adfwi {
+
+namespace {
+
+constexpr int TX = 64, TZ = 16;             // tile interior
+constexpr int HX = 4;                       // x halo of the staged rectangles (one float4 group)
+constexpr int RXH = TX + 2 * HX;            // 72 floats per halo row
+constexpr int NG = TX / 4;                  // float4 groups per tile row
+constexpr int NTH = NG * (TZ / 2);          // 128 threads: float4 x 2 rows each
+constexpr int CMAX = 32;                    // max shots per chunk
+constexpr int CPX = 4, CPZ = 4;             // apron of the coefficient pack
+constexpr int NSTAGE = 2;
+constexpr int CF = TZ * TX;                 // floats of a core (no halo) rectangle
+constexpr int CB = CF * 4;
+
+template <int NN> struct Geo {
+    static constexpr int RZH = TZ + 2 * NN;
+    static constexpr int HF = RZH * RXH;                       // floats of a halo rectangle
+    static constexpr int HB = (HF * 4 + 127) / 128 * 128;      // bytes, 128-B aligned
+    static constexpr int NRING = 2 * NN * (NG + 2) + 2 * TZ;   // float4 groups of the ring around the tile
+    static constexpr int S_STAGE = 4 * HB + 6 * CB;
+    static constexpr int V_STAGE = 3 * HB + 4 * CB;
+    static constexpr int K1_STAGE = 6 * HB;
+    static constexpr int K2_STAGE = 9 * HB;
+};
+constexpr int TAIL_BYTES = 64 + 2 * CMAX * 4 + 3 * CMAX * 4 + 64;   // elf_s: mbarriers + per-shot scalars
+constexpr int TAIL_SMALL = 64 + 2 * CMAX * 4;                       // other kernels: mbarriers + source cells
+
+// plane index of field f, shot s in the workspace's plane array: f*ns + s
+enum { P_VXX = 0, P_VXZ, P_VZX, P_VZZ, P_S0, P_S1, P_S2, P_S3, P_S4, P_S5, P_TXX, P_TZZ, P_TXZ, P_FWD_COUNT,
+       P_LV = P_FWD_COUNT,          // 2 x 4 velocity-split cotangents (ping-pong)
+       P_LS = P_LV + 8,             // 2 x 6 stress-split cotangents (ping-pong)
+       P_LVX = P_LS + 12, P_LVZ,    // cotangents of the velocity sums
+       P_MXX, P_MZZ, P_MXZ,         // cotangents of the stress sums (between elf_k1 and elf_k2)
+       P_COUNT };
+constexpr int NHIST = 8;            // history planes per step: dxb_vx, dzb_vz, dxf_vz, dzf_vx, dxf_txx, dzb_txz, dxb_txz, dzf_tzz
+
+struct EGeom {
+    int nzp, nxp, ld, fs, nt, ns, ntx, ntz, cpld;
+    size_t plane;
+    float dt, dx, dz, dt_dx, dt_dz, half_dt;
+    float rdx, rdz;          // RN(1/dx), RN(1/dz) for fdivs()
+    float c[3];
+};
+struct ECoef { const float *c11, *c13, *c33, *c55, *bx, *bz, *bcx, *bcz; };   // pack planes, pre-offset to cell (0,0)
+struct RcvB { const int* start; const int* id; const int* zx; const unsigned char* nbr; };
+struct Walk { int s_begin, s_end, chunk, nchunks; };
+
+struct SArgs { ECoef cp; const unsigned char* tflags; float* planes; const float* mt; const float* src_v;
+               const int64_t *sx, *sz; float* hist; int hist_len, tl, it; Walk w; };
+struct VArgs { ECoef cp; const unsigned char* tflags; float* planes; float* hist; int hist_len, tl, it;
+               int nr; RcvB rb; float* rcv[5]; Walk w; };
+struct K1Args { ECoef cp; const unsigned char* tflags; float* planes; const float* hist; int hist_len, tl, it, lcur;
+                int nr; RcvB rb; const float* g[5]; float* gpart; Walk w; };
+struct K2Args { ECoef cp; const unsigned char* tflags; float* planes; const float* hist; int hist_len, tl, it, lcur;
+                const float* mt; const int64_t *sx, *sz; float* g_src; float* gpart; Walk w; };
+
+// ---- small device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ uint64_t l2_keep_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldk4(const float* p, uint64_t pol)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red4(float* p, const float4& v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#define F4OP(name, expr)                                                                        \
+    __device__ __forceinline__ float4 name(const float4& a, const float4& b)                    \
+    { float4 r; { const float x = a.x, y = b.x; r.x = (expr); } { const float x = a.y, y = b.y; r.y = (expr); } \
+      { const float x = a.z, y = b.z; r.z = (expr); } { const float x = a.w, y = b.w; r.w = (expr); } return r; }
+F4OP(add4, x + y)
+F4OP(sub4, x - y)
+F4OP(mul4, x * y)
+F4OP(div4, x / y)
+#undef F4OP
+__device__ __forceinline__ float4 muls(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 smul(float s, const float4& a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float4 divs(const float4& a, float s) { return make_float4(a.x / s, a.y / s, a.z / s, a.w / s); }
+// Correctly rounded a / b from a precomputed correctly rounded reciprocal rb = RN(1/b): one multiply and two
+// Newton corrections with exact FMA remainders.  After the first correction q is a faithful rounding of a/b,
+// so the second one returns RN(a/b) (Markstein's theorem) -- the same bits as the IEEE division of the eager
+// reference -- at 5 instructions and with no slow path for zero numerators (the compiler's division sequence
+// takes its out-of-line path for every zero operand, i.e. for every cell the wave has not reached yet).
+// The remainders are exact only away from the underflow / overflow range: numerators with an exponent outside
+// [2^-60, 2^60] (other than zero) take the IEEE division.  Divisors are grid spacings and 1 + dt/2*profile.
+__device__ __forceinline__ float fdiv1(float a, float b, float rb)
+{
+    float q = a * rb;
+    q = __fmaf_rn(__fmaf_rn(-b, q, a), rb, q);
+    q = __fmaf_rn(__fmaf_rn(-b, q, a), rb, q);
+    return q;
+}
+__device__ __forceinline__ bool div_safe1(float a)
+{
+    const unsigned u = __float_as_uint(a) << 1;
+    return (u - (67u << 24) < (121u << 24)) || u == 0u;
+}
+__device__ __forceinline__ bool div_safe4(const float4& a) { return div_safe1(a.x) && div_safe1(a.y) && div_safe1(a.z) && div_safe1(a.w); }
+__device__ __forceinline__ float4 fdiv4(const float4& a, const float4& b, const float4& rb)
+{
+    float4 q = make_float4(fdiv1(a.x, b.x, rb.x), fdiv1(a.y, b.y, rb.y), fdiv1(a.z, b.z, rb.z), fdiv1(a.w, b.w, rb.w));
+    if (!div_safe4(a)) q = make_float4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w);
+    return q;
+}
+__device__ __forceinline__ float4 fdivs(const float4& a, float b, float rb)
+{
+    float4 q = make_float4(fdiv1(a.x, b, rb), fdiv1(a.y, b, rb), fdiv1(a.z, b, rb), fdiv1(a.w, b, rb));
+    if (!div_safe4(a)) q = make_float4(a.x / b, a.y / b, a.z / b, a.w / b);
+    return q;
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 one4() { return make_float4(1.f, 1.f, 1.f, 1.f); }
+__device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+// per-component select: bit x of m set -> a, else b
+__device__ __forceinline__ float4 sel4(unsigned m, const float4& a, const float4& b)
+{ return make_float4((m & 1u) ? a.x : b.x, (m & 2u) ? a.y : b.y, (m & 4u) ? a.z : b.z, (m & 8u) ? a.w : b.w); }
+__device__ __forceinline__ float comp4(const float4& a, int i) { return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w; }
+__device__ __forceinline__ void addc4(float4& a, int i, float v)
+{ if (i == 0) a.x = a.x + v; else if (i == 1) a.y = a.y + v; else if (i == 2) a.z = a.z + v; else a.w = a.w + v; }
+
+// 12-float row segment [c0-4, c0+8) around the thread's float4 (p points at the float4)
+__device__ __forceinline__ void ldseg(const float* p, float* s)
+{
+    const float4 a = ld4(p - 4), b = ld4(p), c = ld4(p + 4);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w; s[8] = c.x; s[9] = c.y; s[10] = c.z; s[11] = c.w;
+}
+__device__ __forceinline__ void ldseg2(const float* p, const float* q, float* s)     // sum of two split fields (p + q, in that order)
+{
+    float a[12], b[12];
+    ldseg(p, a); ldseg(q, b);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = a[i] + b[i];
+}
+// x operators on a segment, cell x of the float4 at seg[4+x].
+//   OFF = 0: backward operator D-x (elastic_kernels.py:86-96): c[k]*(a[k] - a[-k-1])
+//   OFF = 1: forward operator  D+x (:66-76):                   c[k]*(a[k+1] - a[-k])
+template <int NN, int OFF> __device__ __forceinline__ float4 xdiff(const float* s, const float* c)
+{
+    float r[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        float v = c[0] * (s[4 + x + OFF] - s[4 + x - 1 + OFF]);
+#pragma unroll
+        for (int k = 1; k < NN; ++k) v = v + c[k] * (s[4 + x + k + OFF] - s[4 + x - k - 1 + OFF]);
+        r[x] = v;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+// gathers of the operator transposes (m is zero outside the update region):
+//   OFF = 0: (D+x)^T : c[k]*(m[j-k-1] - m[j+k]);   OFF = 1: (D-x)^T : c[k]*(m[j-k] - m[j+k+1])
+template <int NN, int OFF> __device__ __forceinline__ float4 xgath(const float* s, const float* c)
+{
+    float r[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < NN; ++k) v += c[k] * (s[4 + x - k - 1 + OFF] - s[4 + x + k + OFF]);
+        r[x] = v;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+// z operators on a window of 2NN rows w[0..2NN): D-z with w[q] = row i-NN+q, D+z with w[q] = row i-NN+1+q
+template <int NN> __device__ __forceinline__ float4 zdiff(const float4* w, const float* c)
+{
+    float4 v = smul(c[0], sub4(w[NN], w[NN - 1]));
+#pragma unroll
+    for (int k = 1; k < NN; ++k) v = add4(v, smul(c[k], sub4(w[NN + k], w[NN - 1 - k])));
+    return v;
+}
+// (D+z)^T with w[q] = row i-NN+q;  (D-z)^T with w[q] = row i-NN+1+q
+template <int NN> __device__ __forceinline__ float4 zgath(const float4* w, const float* c)
+{
+    float4 v = zero4();
+#pragma unroll
+    for (int k = 0; k < NN; ++k) v = add4(v, smul(c[k], sub4(w[NN - 1 - k], w[NN + k])));
+    return v;
+}
+
+// (tile, shot) sequence of one persistent CTA: items blockIdx.x, +gridDim.x, ...
+struct Cursor {
+    int item, s, s_hi, X0, Z0; bool valid;
+    __device__ __forceinline__ void set(int it, const EGeom& g, const Walk& w)
+    {
+        item = it; valid = it < g.ntx * g.ntz * w.nchunks;
+        if (valid) {
+            const int tile = it / w.nchunks, ch = it - tile * w.nchunks;
+            const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+            X0 = txi * TX; Z0 = tzi * TZ;
+            s = w.s_begin + ch * w.chunk; s_hi = min(s + w.chunk, w.s_end);
+        }
+    }
+    __device__ __forceinline__ void next(const EGeom& g, const Walk& w)
+    {
+        if (valid && ++s >= s_hi) set(item + gridDim.x, g, w);
+    }
+};
+
+// thread roles: float4 group l, rows 2q and 2q+1 of the tile
+struct Roles {
+    int q, l, r0, c0;
+    __device__ __forceinline__ explicit Roles(int tid) { q = tid / NG; l = tid - q * NG; r0 = 2 * q; c0 = 4 * l; }
+};
+// ring float4 group i in [0, NRING): rows [-NN,0) and [TZ,TZ+NN) x groups [-1,NG], rows [0,TZ) x groups {-1,NG}
+template <int NN> __device__ __forceinline__ void ring_cell(int i, int& r, int& gi)
+{
+    constexpr int W = NG + 2;
+    if (i < NN * W) { r = -NN + i / W; gi = i % W - 1; }
+    else if (i < 2 * NN * W) { const int ii = i - NN * W; r = TZ + ii / W; gi = ii % W - 1; }
+    else { const int ii = i - 2 * NN * W; r = ii >> 1; gi = (ii & 1) ? NG : -1; }
+}
+// update-region masks (elastic_kernels.py:303-310): rows/cols [NN, n-NN)
+template <int NN> __device__ __forceinline__ unsigned col_mask(int gx, int nxp)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) if (gx + x >= NN && gx + x < nxp - NN) m |= 1u << x;
+    return m;
+}
+template <int NN> __device__ __forceinline__ bool row_in(int gz, int nzp) { return gz >= NN && gz < nzp - NN; }
+
+#define ELF_WAIT_STAGE(k) do { while (!mbar_try(bar + (k), (par >> (k)) & 1u)) {} par ^= 1u << (k); } while (0)
+
+// ==========================================================================================
+// elf_s : stress update (:341-384 / :497-540)
+// ==========================================================================================
+template <int NN> __device__ __forceinline__ void s_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
+                                                          const CUtensorMap* th, const CUtensorMap* tc, int ns)
+{
+    using G = Geo<NN>;
+    unsigned char* st = smem + k * G::S_STAGE;
+    fence_proxy_async();
+    mbar_expect_tx(bar + k, 4 * G::HF * 4 + 6 * CB);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_VXX + f) * ns + c.s, bar + k);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) tma_load_3d(st + 4 * G::HB + f * CB, tc, c.X0, c.Z0, (P_S0 + f) * ns + c.s, bar + k);
+}
+
+template <int NN, bool PML, bool FS, bool SAVE>
+__device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap* tc, const EGeom& g, const SArgs& a,
+                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                       int* s_sz, int* s_sx, float* s_sxx, float* s_szz, float* s_sxz,
+                                       const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
+{
+    using G = Geo<NN>;
+    const uint64_t pol = l2_keep_policy();
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
+    const unsigned cm = col_mask<NN>(gx, g.nxp);
+    const bool col_ok = gx < g.ld;
+    if (tid < s_hi - s_lo) {         // per-shot scalars (:341-346: -(M/2)*src)
+        const int s = s_lo + tid;
+        const float* M = a.mt + (size_t)s * 9;
+        const float v = a.src_v[(size_t)s * g.nt + a.it];
+        s_sz[tid] = (int)a.sz[s]; s_sx[tid] = (int)a.sx[s];
+        s_sxx[tid] = (-(M[0] / 2.0f)) * v; s_szz[tid] = (-(M[8] / 2.0f)) * v; s_sxz[tid] = (-(M[2] / 2.0f)) * v;
+    }
+    float4 C11[2], C13[2], C33[2], C55[2], PXN[2], PXI[2], PZN[2], PZI[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
+        C11[j] = ldk4(a.cp.c11 + o, pol); C13[j] = ldk4(a.cp.c13 + o, pol);
+        C33[j] = ldk4(a.cp.c33 + o, pol); C55[j] = ldk4(a.cp.c55 + o, pol);
+        if (PML) {
+            const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+            const float4 pxd = add4(one4(), smul(g.half_dt, bx_)), pzd = add4(one4(), smul(g.half_dt, bz_));
+            PXN[j] = sub4(one4(), smul(g.half_dt, bx_)); PZN[j] = sub4(one4(), smul(g.half_dt, bz_));
+            PXI[j] = div4(one4(), pxd); PZI[j] = div4(one4(), pzd);
+        }
+    }
+    if (first) {
+        griddep_wait();
+#pragma unroll
+        for (int k = 0; k < NSTAGE; ++k)
+            if (pc.valid) { if (tid == 0) s_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+    }
+    __syncthreads();
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = stage;
+        float* hv = (float*)(smem + k * G::S_STAGE);                    // 4 halo rects: vxx, vxz, vzx, vzz
+        const float* cs = (const float*)(smem + k * G::S_STAGE + 4 * G::HB);   // 6 core rects
+        float* vxx = hv; float* vxz = hv + G::HB / 4; float* vzx = hv + 2 * (G::HB / 4); float* vzz = hv + 3 * (G::HB / 4);
+        const int szs = s_sz[s - s_lo], sxs = s_sx[s - s_lo];
+        ELF_WAIT_STAGE(k);
+        if (FS && tzi == 0) {
+            // free-surface velocity rows (:399-402), formed from the sums of rows h-1, h of the previous step:
+            // vz[h-2] = vz[h-3] = vz[h-1]; vx[h-2] = vz[h-2,j+1] - vz[h-2,j] + vz[h-1,j+1] - vz[h-1,j] + vx[h,j]
+            // (rows h-2, h-3 are outside the update region: their split fields are zero, so the edit
+            //  is parked in the first split of each pair)
+            const int t = tid;
+            if (t >= 1 && t < RXH - 1) {
+                const int j = X0 + t - HX;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (2 * NN) * RXH + t, rh = (2 * NN + 1) * RXH + t, rh2 = (2 * NN - 1) * RXH + t, rh3 = (2 * NN - 2) * RXH + t;
+                    const float vz1 = vzx[rh1] + vzz[rh1];
+                    const float vz1n = (j + 1 < g.nxp - NN) ? vzx[rh1 + 1] + vzz[rh1 + 1] : 0.f;
+                    const float vxh = vxx[rh] + vxz[rh];
+                    const float nvx = (((vz1n - vz1) + vz1n) - vz1) + vxh;
+                    vzx[rh2] = vz1; vzz[rh2] = 0.f; vzx[rh3] = vz1; vzz[rh3] = 0.f;
+                    vxx[rh2] = nvx; vxz[rh2] = 0.f;
+                }
+            }
+            __syncthreads();
+        }
+        const bool has_src = (szs >= Z0) && (szs < Z0 + TZ) && (sxs >= X0) && (sxs < X0 + TX);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = R.r0 + j, gz = gz0 + j;
+            const int hb = (r + NN) * RXH + R.c0 + HX;
+            float sx_[12], sz_[12];
+            ldseg2(vxx + hb, vxz + hb, sx_);
+            ldseg2(vzx + hb, vzz + hb, sz_);
+            float4 wzb[2 * NN], wzf[2 * NN];
+#pragma unroll
+            for (int q = 0; q < 2 * NN; ++q) {
+                wzb[q] = add4(ld4(vzx + hb + (q - NN) * RXH), ld4(vzz + hb + (q - NN) * RXH));           // vz rows r-NN .. r+NN-1
+                wzf[q] = add4(ld4(vxx + hb + (q - NN + 1) * RXH), ld4(vxz + hb + (q - NN + 1) * RXH));   // vx rows r-NN+1 .. r+NN
+            }
+            const float4 dxb_vx = xdiff<NN, 0>(sx_, g.c), dxf_vz = xdiff<NN, 1>(sz_, g.c);
+            const float4 dzb_vz = zdiff<NN>(wzb, g.c), dzf_vx = zdiff<NN>(wzf, g.c);
+            const int co = r * TX + R.c0;
+            float4 a0 = ld4(cs + co), a1 = ld4(cs + CF + co), a2 = ld4(cs + 2 * CF + co);
+            float4 a3 = ld4(cs + 3 * CF + co), a4 = ld4(cs + 4 * CF + co), a5 = ld4(cs + 5 * CF + co);
+            const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
+            float4 n0, n1, n2, n3, n4, n5;
+            if (PML) {
+                n0 = mul4(add4(mul4(PXN[j], a0), smul(g.dt_dx, mul4(C11[j], dxb_vx))), PXI[j]);
+                n1 = mul4(add4(mul4(PZN[j], a1), smul(g.dt_dz, mul4(C13[j], dzb_vz))), PZI[j]);
+                n2 = mul4(add4(mul4(PXN[j], a2), smul(g.dt_dx, mul4(C13[j], dxb_vx))), PXI[j]);
+                n3 = mul4(add4(mul4(PZN[j], a3), smul(g.dt_dz, mul4(C33[j], dzb_vz))), PZI[j]);
+                n4 = mul4(add4(mul4(PXN[j], a4), smul(g.dt_dx, mul4(C55[j], dxf_vz))), PXI[j]);
+                n5 = mul4(add4(mul4(PZN[j], a5), smul(g.dt_dz, mul4(C55[j], dzf_vx))), PZI[j]);
+            } else {
+                n0 = add4(a0, smul(g.dt_dx, mul4(C11[j], dxb_vx)));
+                n1 = add4(a1, smul(g.dt_dz, mul4(C13[j], dzb_vz)));
+                n2 = add4(a2, smul(g.dt_dx, mul4(C13[j], dxb_vx)));
+                n3 = add4(a3, smul(g.dt_dz, mul4(C33[j], dzb_vz)));
+                n4 = add4(a4, smul(g.dt_dx, mul4(C55[j], dxf_vz)));
+                n5 = add4(a5, smul(g.dt_dz, mul4(C55[j], dzf_vx)));
+            }
+            a0 = sel4(m, n0, a0); a1 = sel4(m, n1, a1); a2 = sel4(m, n2, a2);
+            a3 = sel4(m, n3, a3); a4 = sel4(m, n4, a4); a5 = sel4(m, n5, a5);
+            if (has_src && szs == gz && !(FS && gz < NN)) {
+                const int dc = sxs - gx;
+                if (dc >= 0 && dc < 4) {
+                    const float sxx = s_sxx[s - s_lo], szz = s_szz[s - s_lo], sxz = s_sxz[s - s_lo];
+                    addc4(a0, dc, sxx); addc4(a1, dc, sxx); addc4(a2, dc, szz); addc4(a3, dc, szz); addc4(a4, dc, sxz); addc4(a5, dc, sxz);
+                }
+            }
+            if (col_ok && gz < g.nzp) {
+                const size_t o = (size_t)gz * g.ld + gx;
+                float* P = a.planes + (size_t)s * g.plane + o;
+                const size_t fp = (size_t)g.ns * g.plane;
+                st4(P + (P_S0 + 0) * fp, a0); st4(P + (P_S0 + 1) * fp, a1); st4(P + (P_S0 + 2) * fp, a2);
+                st4(P + (P_S0 + 3) * fp, a3); st4(P + (P_S0 + 4) * fp, a4); st4(P + (P_S0 + 5) * fp, a5);
+                st4(P + P_TXX * fp, add4(a0, a1)); st4(P + P_TZZ * fp, add4(a2, a3)); st4(P + P_TXZ * fp, add4(a4, a5));
+                if (SAVE) {
+                    float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + o;
+                    __stcs(reinterpret_cast<float4*>(H), sel4(m, dxb_vx, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_vz, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxf_vz, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_vx, zero4()));
+                }
+            }
+        }
+        if (FS && tzi == 0) fence_proxy_async();
+        __syncthreads();
+        if (pc.valid) { if (tid == 0) s_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+}
+
+template <int NN, bool FS, bool SAVE>
+__global__ void __launch_bounds__(NTH, 2)
+elf_s(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap tc, const EGeom g, const SArgs a)
+{
+    using G = Geo<NN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = (uint64_t*)(smem + NSTAGE * G::S_STAGE);
+    int* s_sz = (int*)(bar + 8);
+    int* s_sx = s_sz + CMAX;
+    float* s_sxx = (float*)(s_sx + CMAX);
+    float* s_szz = s_sxx + CMAX;
+    float* s_sxz = s_szz + CMAX;
+    const int tid = threadIdx.x;
+    if (tid == 0) { for (int k = 0; k < NSTAGE; ++k) mbar_init(bar + k, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    int stage = 0;
+    const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    Cursor pc;
+    pc.set(blockIdx.x, g, a.w);
+    griddep_launch_dependents();
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
+        const int s_lo = a.w.s_begin + chunk * a.w.chunk;
+        const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
+        const bool first = item == (int)blockIdx.x;
+        if (a.tflags[tile]) s_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        else                s_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        __syncthreads();
+    }
+}
+
+// ==========================================================================================
+// elf_v : velocity update + receivers (:387-409 / :543-565)
+// ==========================================================================================
+template <int NN> __device__ __forceinline__ void v_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
+                                                          const CUtensorMap* th, const CUtensorMap* tc, int ns)
+{
+    using G = Geo<NN>;
+    unsigned char* st = smem + k * G::V_STAGE;
+    fence_proxy_async();
+    mbar_expect_tx(bar + k, 3 * G::HF * 4 + 4 * CB);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_TXX + f) * ns + c.s, bar + k);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) tma_load_3d(st + 3 * G::HB + f * CB, tc, c.X0, c.Z0, (P_VXX + f) * ns + c.s, bar + k);
+}
+
+template <int NN, bool PML, bool FS, bool SAVE>
+__device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap* tc, const EGeom& g, const VArgs& a,
+                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                       const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
+{
+    using G = Geo<NN>;
+    const uint64_t pol = l2_keep_policy();
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
+    const unsigned cm = col_mask<NN>(gx, g.nxp);
+    const bool col_ok = gx < g.ld;
+    float4 DBX[2], DBZ[2], PXN[2], PXD[2], PZN[2], PZD[2], RPXD[2], RPZD[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
+        DBX[j] = smul(g.dt, ldk4(a.cp.bx + o, pol)); DBZ[j] = smul(g.dt, ldk4(a.cp.bz + o, pol));     // dt*bx, dt*bz (:387-394)
+        if (PML) {
+            const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+            PXD[j] = add4(one4(), smul(g.half_dt, bx_)); PZD[j] = add4(one4(), smul(g.half_dt, bz_));
+            PXN[j] = sub4(one4(), smul(g.half_dt, bx_)); PZN[j] = sub4(one4(), smul(g.half_dt, bz_));
+            RPXD[j] = div4(one4(), PXD[j]); RPZD[j] = div4(one4(), PZD[j]);
+        }
+    }
+    const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
+    const bool has_rcv = rcv_hi > rcv_lo;
+    if (first) {
+        griddep_wait();
+#pragma unroll
+        for (int k = 0; k < NSTAGE; ++k)
+            if (pc.valid) { if (tid == 0) v_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+    }
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = stage;
+        float* ht = (float*)(smem + k * G::V_STAGE);                     // 3 halo rects: txx, tzz, txz
+        float* cv = (float*)(smem + k * G::V_STAGE + 3 * G::HB);         // 4 core rects: vxx, vxz, vzx, vzz
+        float* txx = ht; float* tzz = ht + G::HB / 4; float* txz = ht + 2 * (G::HB / 4);
+        ELF_WAIT_STAGE(k);
+        if (FS && tzi == 0) {          // free-surface stress rows (:380-384) on the staged sums
+            const int t = tid;
+            if (t < RXH) {
+                const int j = X0 + t - HX;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (2 * NN) * RXH + t, rh = (2 * NN + 1) * RXH + t, rh2 = (2 * NN - 1) * RXH + t, rh3 = (2 * NN - 2) * RXH + t;
+                    tzz[rh1] = 0.f;
+                    txz[rh2] = -txz[rh1];
+                    tzz[rh2] = -tzz[rh];
+                    txz[rh3] = -txz[rh];
+                }
+            }
+            __syncthreads();
+        }
+        float4 nvx[2], nvz[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = R.r0 + j, gz = gz0 + j;
+            const int hb = (r + NN) * RXH + R.c0 + HX;
+            float sxx_[12], sxz_[12];
+            ldseg(txx + hb, sxx_);
+            ldseg(txz + hb, sxz_);
+            float4 wzb[2 * NN], wzf[2 * NN];
+#pragma unroll
+            for (int q = 0; q < 2 * NN; ++q) {
+                wzb[q] = ld4(txz + hb + (q - NN) * RXH);          // txz rows r-NN .. r+NN-1
+                wzf[q] = ld4(tzz + hb + (q - NN + 1) * RXH);      // tzz rows r-NN+1 .. r+NN
+            }
+            const float4 dxf_txx = xdiff<NN, 1>(sxx_, g.c), dxb_txz = xdiff<NN, 0>(sxz_, g.c);
+            const float4 dzb_txz = zdiff<NN>(wzb, g.c), dzf_tzz = zdiff<NN>(wzf, g.c);
+            const int co = r * TX + R.c0;
+            float4 q0 = ld4(cv + co), q1 = ld4(cv + CF + co), q2 = ld4(cv + 2 * CF + co), q3 = ld4(cv + 3 * CF + co);
+            const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
+            float4 n0, n1, n2, n3;
+            if (PML) {
+                n0 = fdiv4(add4(mul4(PXN[j], q0), fdivs(mul4(DBX[j], dxf_txx), g.dx, g.rdx)), PXD[j], RPXD[j]);
+                n1 = fdiv4(add4(mul4(PZN[j], q1), fdivs(mul4(DBX[j], dzb_txz), g.dz, g.rdz)), PZD[j], RPZD[j]);
+                n2 = fdiv4(add4(mul4(PXN[j], q2), fdivs(mul4(DBZ[j], dxb_txz), g.dx, g.rdx)), PXD[j], RPXD[j]);
+                n3 = fdiv4(add4(mul4(PZN[j], q3), fdivs(mul4(DBZ[j], dzf_tzz), g.dz, g.rdz)), PZD[j], RPZD[j]);
+            } else {
+                n0 = add4(q0, fdivs(mul4(DBX[j], dxf_txx), g.dx, g.rdx));
+                n1 = add4(q1, fdivs(mul4(DBX[j], dzb_txz), g.dz, g.rdz));
+                n2 = add4(q2, fdivs(mul4(DBZ[j], dxb_txz), g.dx, g.rdx));
+                n3 = add4(q3, fdivs(mul4(DBZ[j], dzf_tzz), g.dz, g.rdz));
+            }
+            q0 = sel4(m, n0, q0); q1 = sel4(m, n1, q1); q2 = sel4(m, n2, q2); q3 = sel4(m, n3, q3);
+            nvx[j] = add4(q0, q1); nvz[j] = add4(q2, q3);
+            if (col_ok && gz < g.nzp) {
+                const size_t o = (size_t)gz * g.ld + gx;
+                float* P = a.planes + (size_t)s * g.plane + o;
+                const size_t fp = (size_t)g.ns * g.plane;
+                st4(P + P_VXX * fp, q0); st4(P + P_VXZ * fp, q1); st4(P + P_VZX * fp, q2); st4(P + P_VZZ * fp, q3);
+                if (SAVE) {
+                    float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + o;
+                    __stcs(reinterpret_cast<float4*>(H), sel4(m, dxf_txx, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_txz, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxb_txz, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_tzz, zero4()));
+                }
+            }
+        }
+        if (has_rcv) {                 // receivers of this tile (:405-409): new sums parked in the vxx / vzx rects
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { const int co = (R.r0 + j) * TX + R.c0; st4(cv + co, nvx[j]); st4(cv + 2 * CF + co, nvz[j]); }
+            __syncthreads();
+            for (int i = rcv_lo + tid; i < rcv_hi; i += NTH) {
+                const int r = a.rb.id[i], zx = a.rb.zx[i];
+                const int z = (zx >> 16) - Z0, x = (zx & 0xffff) - X0;
+                const int oh = (z + NN) * RXH + x + HX, oc = z * TX + x;
+                const size_t o = ((size_t)s * g.nt + a.it) * a.nr + r;
+                a.rcv[0][o] = txx[oh]; a.rcv[1][o] = tzz[oh]; a.rcv[2][o] = txz[oh];
+                a.rcv[3][o] = cv[oc]; a.rcv[4][o] = cv[2 * CF + oc];
+            }
+        }
+        if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
+        __syncthreads();
+        if (pc.valid) { if (tid == 0) v_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+}
+
+template <int NN, bool FS, bool SAVE>
+__global__ void __launch_bounds__(NTH, 2)
+elf_v(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap tc, const EGeom g, const VArgs a)
+{
+    using G = Geo<NN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = (uint64_t*)(smem + NSTAGE * G::V_STAGE);
+    const int tid = threadIdx.x;
+    if (tid == 0) { for (int k = 0; k < NSTAGE; ++k) mbar_init(bar + k, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    int stage = 0;
+    const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    Cursor pc;
+    pc.set(blockIdx.x, g, a.w);
+    griddep_launch_dependents();
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
+        const int s_lo = a.w.s_begin + chunk * a.w.chunk;
+        const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
+        const bool first = item == (int)blockIdx.x;
+        if (a.tflags[tile]) v_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, R, tid, tile, s_lo, s_hi, first);
+        else                v_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, R, tid, tile, s_lo, s_hi, first);
+        __syncthreads();
+    }
+}
+
+// ==========================================================================================
+// elf_k1 : adjoint of the velocity update
+// ==========================================================================================
+template <int NN> __device__ __forceinline__ void k1_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
+                                                           const CUtensorMap* th, int ns, int lcur)
+{
+    using G = Geo<NN>;
+    unsigned char* st = smem + k * G::K1_STAGE;
+    fence_proxy_async();
+    mbar_expect_tx(bar + k, 6 * G::HF * 4);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LV + 4 * lcur + f) * ns + c.s, bar + k);
+    tma_load_3d(st + 4 * G::HB, th, c.X0 - HX, c.Z0 - NN, P_LVX * ns + c.s, bar + k);
+    tma_load_3d(st + 5 * G::HB, th, c.X0 - HX, c.Z0 - NN, P_LVZ * ns + c.s, bar + k);
+}
+
+// own-cell transpose of the velocity update for one float4 group (all in registers)
+template <bool PML>
+__device__ __forceinline__ void k1_cell(const EGeom& g, unsigned m, const float4& L0, const float4& L1, const float4& L2, const float4& L3,
+                                        const float4& lvx, const float4& lvz, const float4& bx, const float4& bz,
+                                        const float4& pxn, const float4& pxd, const float4& pzn, const float4& pzd,
+                                        const float4& rpxd, const float4& rpzd,
+                                        float4& w1, float4& w2, float4& w3, float4& w4,
+                                        float4& m1, float4& m2, float4& m3, float4& m4,
+                                        float4& N0, float4& N1, float4& N2, float4& N3)
+{
+    const float4 q1 = add4(L0, lvx), q2 = add4(L1, lvx), q3 = add4(L2, lvz), q4 = add4(L3, lvz);
+    if (PML) {
+        w1 = fdiv4(fdivs(muls(q1, g.dt), g.dx, g.rdx), pxd, rpxd); w2 = fdiv4(fdivs(muls(q2, g.dt), g.dz, g.rdz), pzd, rpzd);
+        w3 = fdiv4(fdivs(muls(q3, g.dt), g.dx, g.rdx), pxd, rpxd); w4 = fdiv4(fdivs(muls(q4, g.dt), g.dz, g.rdz), pzd, rpzd);
+        N0 = fdiv4(mul4(pxn, q1), pxd, rpxd); N1 = fdiv4(mul4(pzn, q2), pzd, rpzd);
+        N2 = fdiv4(mul4(pxn, q3), pxd, rpxd); N3 = fdiv4(mul4(pzn, q4), pzd, rpzd);
+    } else {
+        w1 = fdivs(muls(q1, g.dt), g.dx, g.rdx); w2 = fdivs(muls(q2, g.dt), g.dz, g.rdz);
+        w3 = fdivs(muls(q3, g.dt), g.dx, g.rdx); w4 = fdivs(muls(q4, g.dt), g.dz, g.rdz);
+        N0 = q1; N1 = q2; N2 = q3; N3 = q4;
+    }
+    w1 = sel4(m, w1, zero4()); w2 = sel4(m, w2, zero4()); w3 = sel4(m, w3, zero4()); w4 = sel4(m, w4, zero4());
+    m1 = mul4(w1, bx); m2 = mul4(w2, bx); m3 = mul4(w3, bz); m4 = mul4(w4, bz);
+    N0 = sel4(m, N0, L0); N1 = sel4(m, N1, L1); N2 = sel4(m, N2, L2); N3 = sel4(m, N3, L3);
+}
+
+template <int NN, bool PML, bool FS>
+__device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, const K1Args& a,
+                                        unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                        const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
+{
+    using G = Geo<NN>;
+    const uint64_t pol = l2_keep_policy();
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
+    const unsigned cm = col_mask<NN>(gx, g.nxp);
+    const bool col_ok = gx < g.ld;
+    const size_t fp = (size_t)g.ns * g.plane;
+    float4 BX[2], BZ[2], PXN[2], PXD[2], PZN[2], PZD[2], RPXD[2], RPZD[2], GBX[2], GBZ[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
+        BX[j] = ldk4(a.cp.bx + o, pol); BZ[j] = ldk4(a.cp.bz + o, pol);
+        if (PML) {
+            const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+            PXD[j] = add4(one4(), smul(g.half_dt, bx_)); PZD[j] = add4(one4(), smul(g.half_dt, bz_));
+            PXN[j] = sub4(one4(), smul(g.half_dt, bx_)); PZN[j] = sub4(one4(), smul(g.half_dt, bz_));
+            RPXD[j] = div4(one4(), PXD[j]); RPZD[j] = div4(one4(), PZD[j]);
+        } else { PXD[j] = PZD[j] = PXN[j] = PZN[j] = RPXD[j] = RPZD[j] = one4(); }
+        GBX[j] = zero4(); GBZ[j] = zero4();
+    }
+    const bool have_gv = a.nr > 0 && (a.g[3] || a.g[4]);
+    const bool have_gs = a.nr > 0 && (a.g[0] || a.g[1] || a.g[2]);
+    const bool inject_v = have_gv && a.rb.nbr[tile];
+    const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
+    const bool inject_s = have_gs && rcv_hi > rcv_lo;
+    if (first) {
+        griddep_wait();
+#pragma unroll
+        for (int k = 0; k < NSTAGE; ++k)
+            if (pc.valid) { if (tid == 0) k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+    }
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = stage;
+        float* L = (float*)(smem + k * G::K1_STAGE);       // rects 0..3: velocity-split cotangents (become m1..m4), 4: lvx, 5: lvz
+        float* lvx = L + 4 * (G::HB / 4); float* lvz = L + 5 * (G::HB / 4);
+        // history of this step (own cells): e1 = D+x txx, e2 = D-z txz, e3 = D-x txz, e4 = D+z tzz
+        float4 E[4][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gz = gz0 + j;
+            const float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + (size_t)gz * g.ld + gx;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                E[e][j] = (col_ok && gz < g.nzp) ? __ldcs(reinterpret_cast<const float4*>(H + (size_t)e * g.plane)) : zero4();
+        }
+        ELF_WAIT_STAGE(k);
+        if (inject_v) {          // 10T: cotangents of the vx / vz records into the staged sums (duplicates legal)
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int tz2 = tzi + dz;
+                if (tz2 < 0 || tz2 >= g.ntz) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int tx2 = txi + dx;
+                    if (tx2 < 0 || tx2 >= g.ntx) continue;
+                    const int t2 = tz2 * g.ntx + tx2;
+                    const int lo = a.rb.start[t2], hi = a.rb.start[t2 + 1];
+                    for (int i = lo + tid; i < hi; i += NTH) {
+                        const int zx = a.rb.zx[i];
+                        const int z = (zx >> 16) - (Z0 - NN), x = (zx & 0xffff) - (X0 - HX);
+                        if (z >= 0 && z < G::RZH && x >= 0 && x < RXH) {
+                            const size_t o = ((size_t)s * g.nt + a.it) * a.nr + a.rb.id[i];
+                            if (a.g[3]) atomicAdd(lvx + z * RXH + x, a.g[3][o]);
+                            if (a.g[4]) atomicAdd(lvz + z * RXH + x, a.g[4][o]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (FS && tzi == 0) {    // 9T: transpose of the free-surface velocity edits (adds into rows h-1, h)
+            const int t = tid;
+            if (t >= 1 && t < RXH) {
+                const int j = X0 + t - HX;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (2 * NN) * RXH + t, rh = (2 * NN + 1) * RXH + t, rh2 = (2 * NN - 1) * RXH + t, rh3 = (2 * NN - 2) * RXH + t;
+                    const float qj = lvx[rh2];
+                    const float qm = (j - 1 >= NN) ? lvx[rh2 - 1] : 0.f;
+                    const float add_vz = lvz[rh2] + lvz[rh3] + 2.0f * (qm - qj);
+                    lvz[rh1] += add_vz;
+                    lvx[rh] += qj;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- pass A: own-cell transpose; m1..m4 replace the split cotangents in the staged rects ------
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = R.r0 + j, gz = gz0 + j;
+            const int hb = (r + NN) * RXH + R.c0 + HX;
+            const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
+            const float4 L0 = ld4(L + hb), L1 = ld4(L + G::HB / 4 + hb), L2 = ld4(L + 2 * (G::HB / 4) + hb), L3 = ld4(L + 3 * (G::HB / 4) + hb);
+            float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
+            k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + hb), ld4(lvz + hb), BX[j], BZ[j], PXN[j], PXD[j], PZN[j], PZD[j], RPXD[j], RPZD[j],
+                         w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
+            st4(L + hb, m1); st4(L + G::HB / 4 + hb, m2); st4(L + 2 * (G::HB / 4) + hb, m3); st4(L + 3 * (G::HB / 4) + hb, m4);
+            GBX[j] = add4(GBX[j], add4(mul4(w1, E[0][j]), mul4(w2, E[1][j])));
+            GBZ[j] = add4(GBZ[j], add4(mul4(w3, E[2][j]), mul4(w4, E[3][j])));
+            if (col_ok && gz < g.nzp) {
+                float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LV + 4 * (a.lcur ^ 1)) * fp;
+                st4(P, N0); st4(P + fp, N1); st4(P + 2 * fp, N2); st4(P + 3 * fp, N3);
+            }
+        }
+        for (int i = tid; i < G::NRING; i += NTH) {     // ring: m only (coefficients from the L2-resident pack)
+            int r, gi;
+            ring_cell<NN>(i, r, gi);
+            const int gzr = Z0 + r, gxr = X0 + 4 * gi;
+            const int hb = (r + NN) * RXH + 4 * gi + HX;
+            const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
+            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
+            float4 pxn = one4(), pxd = one4(), pzn = one4(), pzd = one4(), rpxd = one4(), rpzd = one4();
+            if (PML) {
+                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+                pxd = add4(one4(), smul(g.half_dt, bx_)); pzd = add4(one4(), smul(g.half_dt, bz_));
+                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
+                rpxd = div4(one4(), pxd); rpzd = div4(one4(), pzd);
+            }
+            const float4 L0 = ld4(L + hb), L1 = ld4(L + G::HB / 4 + hb), L2 = ld4(L + 2 * (G::HB / 4) + hb), L3 = ld4(L + 3 * (G::HB / 4) + hb);
+            float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
+            k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + hb), ld4(lvz + hb), ldk4(a.cp.bx + o, pol), ldk4(a.cp.bz + o, pol), pxn, pxd, pzn, pzd, rpxd, rpzd,
+                         w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
+            st4(L + hb, m1); st4(L + G::HB / 4 + hb, m2); st4(L + 2 * (G::HB / 4) + hb, m3); st4(L + 3 * (G::HB / 4) + hb, m4);
+        }
+        __syncthreads();
+        // ---- pass B: 6T gathers -> cotangents of the stress sums -----------------------------------
+        {
+            const float* M1 = L; const float* M2 = L + G::HB / 4; const float* M3 = L + 2 * (G::HB / 4); const float* M4 = L + 3 * (G::HB / 4);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = R.r0 + j, gz = gz0 + j;
+                const int hb = (r + NN) * RXH + R.c0 + HX;
+                float s1[12], s3[12];
+                ldseg(M1 + hb, s1); ldseg(M3 + hb, s3);
+                float4 w2[2 * NN], w4[2 * NN];
+#pragma unroll
+                for (int q = 0; q < 2 * NN; ++q) {
+                    w2[q] = ld4(M2 + hb + (q - NN + 1) * RXH);      // (D-z)^T: rows i-NN+1 .. i+NN
+                    w4[q] = ld4(M4 + hb + (q - NN) * RXH);          // (D+z)^T: rows i-NN .. i+NN-1
+                }
+                const float4 mxx = xgath<NN, 0>(s1, g.c);
+                const float4 mxz = add4(zgath<NN>(w2, g.c), xgath<NN, 1>(s3, g.c));
+                const float4 mzz = zgath<NN>(w4, g.c);
+                if (col_ok && gz < g.nzp) {
+                    float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx;
+                    st4(P + P_MXX * fp, mxx); st4(P + P_MZZ * fp, mzz); st4(P + P_MXZ * fp, mxz);
+                }
+            }
+        }
+        if (inject_s) {          // 10T: cotangents of the stress records add to the sums' cotangents of this tile's cells
+            __syncthreads();
+            for (int i = rcv_lo + tid; i < rcv_hi; i += NTH) {
+                const int zx = a.rb.zx[i];
+                const size_t o = ((size_t)s * g.nt + a.it) * a.nr + a.rb.id[i];
+                float* P = a.planes + (size_t)s * g.plane + (size_t)(zx >> 16) * g.ld + (zx & 0xffff);
+                if (a.g[0]) atomicAdd(P + P_MXX * fp, a.g[0][o]);
+                if (a.g[1]) atomicAdd(P + P_MZZ * fp, a.g[1][o]);
+                if (a.g[2]) atomicAdd(P + P_MXZ * fp, a.g[2][o]);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (pc.valid) { if (tid == 0) k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int gz = gz0 + j;
+        if (col_ok && gz < g.nzp) {
+            float* gp = a.gpart + (size_t)chunk * 6 * g.plane + (size_t)gz * g.ld + gx;
+            red4(gp + 4 * g.plane, GBX[j]); red4(gp + 5 * g.plane, GBZ[j]);
+        }
+    }
+}
+
+template <int NN, bool FS>
+__global__ void __launch_bounds__(NTH, 2)
+elf_k1(const __grid_constant__ CUtensorMap th, const EGeom g, const K1Args a)
+{
+    using G = Geo<NN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = (uint64_t*)(smem + NSTAGE * G::K1_STAGE);
+    const int tid = threadIdx.x;
+    if (tid == 0) { for (int k = 0; k < NSTAGE; ++k) mbar_init(bar + k, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    int stage = 0;
+    const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    Cursor pc;
+    pc.set(blockIdx.x, g, a.w);
+    griddep_launch_dependents();
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
+        const int s_lo = a.w.s_begin + chunk * a.w.chunk;
+        const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
+        const bool first = item == (int)blockIdx.x;
+        if (a.tflags[tile]) k1_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                k1_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, R, tid, tile, chunk, s_lo, s_hi, first);
+        __syncthreads();
+    }
+}
+
+// ==========================================================================================
+// elf_k2 : adjoint of the stress update (Appendix A.2, steps 5T..1T)
+// ==========================================================================================
+template <int NN> __device__ __forceinline__ void k2_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
+                                                           const CUtensorMap* th, int ns, int lcur)
+{
+    using G = Geo<NN>;
+    unsigned char* st = smem + k * G::K2_STAGE;
+    fence_proxy_async();
+    mbar_expect_tx(bar + k, 9 * G::HF * 4);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_MXX + f) * ns + c.s, bar + k);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) tma_load_3d(st + (3 + f) * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LS + 6 * lcur + f) * ns + c.s, bar + k);
+}
+
+template <bool PML>
+__device__ __forceinline__ void k2_cell(const EGeom& g, unsigned m, const float4* LS, const float4& mxx, const float4& mzz, const float4& mxz,
+                                        const float4& c11, const float4& c13, const float4& c33, const float4& c55,
+                                        const float4& pxn, const float4& pxi, const float4& pzn, const float4& pzi,
+                                        float4* l, float4* q, float4& nA, float4& nB, float4& nC, float4& nD, float4* N)
+{
+    l[0] = add4(LS[0], mxx); l[1] = add4(LS[1], mxx); l[2] = add4(LS[2], mzz);
+    l[3] = add4(LS[3], mzz); l[4] = add4(LS[4], mxz); l[5] = add4(LS[5], mxz);
+    float4 t[6];
+    if (PML) {
+        t[0] = mul4(l[0], pxi); t[1] = mul4(l[1], pzi); t[2] = mul4(l[2], pxi); t[3] = mul4(l[3], pzi); t[4] = mul4(l[4], pxi); t[5] = mul4(l[5], pzi);
+        N[0] = mul4(pxn, t[0]); N[1] = mul4(pzn, t[1]); N[2] = mul4(pxn, t[2]); N[3] = mul4(pzn, t[3]); N[4] = mul4(pxn, t[4]); N[5] = mul4(pzn, t[5]);
+    } else {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) { t[f] = l[f]; N[f] = l[f]; }
+    }
+    q[0] = sel4(m, muls(t[0], g.dt_dx), zero4()); q[1] = sel4(m, muls(t[1], g.dt_dz), zero4());
+    q[2] = sel4(m, muls(t[2], g.dt_dx), zero4()); q[3] = sel4(m, muls(t[3], g.dt_dz), zero4());
+    q[4] = sel4(m, muls(t[4], g.dt_dx), zero4()); q[5] = sel4(m, muls(t[5], g.dt_dz), zero4());
+    nA = add4(mul4(q[0], c11), mul4(q[2], c13));
+    nB = add4(mul4(q[1], c13), mul4(q[3], c33));
+    nC = mul4(q[4], c55);
+    nD = mul4(q[5], c55);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) N[f] = sel4(m, N[f], LS[f]);
+}
+
+template <int NN, bool PML, bool FS>
+__device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, const K2Args& a,
+                                        unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                        int* s_sz, int* s_sx, const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
+{
+    using G = Geo<NN>;
+    constexpr int HQ = G::HB / 4;
+    const uint64_t pol = l2_keep_policy();
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
+    const unsigned cm = col_mask<NN>(gx, g.nxp);
+    const bool col_ok = gx < g.ld;
+    const size_t fp = (size_t)g.ns * g.plane;
+    if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
+    float4 C11[2], C13[2], C33[2], C55[2], PXN[2], PXI[2], PZN[2], PZI[2], G11[2], G13[2], G33[2], G55[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
+        C11[j] = ldk4(a.cp.c11 + o, pol); C13[j] = ldk4(a.cp.c13 + o, pol);
+        C33[j] = ldk4(a.cp.c33 + o, pol); C55[j] = ldk4(a.cp.c55 + o, pol);
+        if (PML) {
+            const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+            const float4 pxd = add4(one4(), smul(g.half_dt, bx_)), pzd = add4(one4(), smul(g.half_dt, bz_));
+            PXN[j] = sub4(one4(), smul(g.half_dt, bx_)); PZN[j] = sub4(one4(), smul(g.half_dt, bz_));
+            PXI[j] = div4(one4(), pxd); PZI[j] = div4(one4(), pzd);
+        } else { PXN[j] = PZN[j] = PXI[j] = PZI[j] = one4(); }
+        G11[j] = zero4(); G13[j] = zero4(); G33[j] = zero4(); G55[j] = zero4();
+    }
+    if (first) {
+        griddep_wait();
+#pragma unroll
+        for (int k = 0; k < NSTAGE; ++k)
+            if (pc.valid) { if (tid == 0) k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+    }
+    __syncthreads();
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = stage;
+        float* MS = (float*)(smem + k * G::K2_STAGE);      // rects 0..2: mxx, mzz, mxz; 3..8: stress-split cotangents
+        float* mzz_r = MS + HQ; float* mxz_r = MS + 2 * HQ;
+        float* LSr = MS + 3 * HQ;                           // rects LS0, LS1, LS4, LS5 become nA, nB, nC, nD
+        // history of this step (own cells): D-x vx, D-z vz, D+x vz, D+z vx
+        float4 D[4][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gz = gz0 + j;
+            const float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + (size_t)gz * g.ld + gx;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                D[e][j] = (col_ok && gz < g.nzp) ? __ldcs(reinterpret_cast<const float4*>(H + (size_t)e * g.plane)) : zero4();
+        }
+        ELF_WAIT_STAGE(k);
+        if (FS && tzi == 0) {    // 5T: transpose of the free-surface stress mirrors
+            const int t = tid;
+            if (t < RXH) {
+                const int j = X0 + t - HX;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (2 * NN) * RXH + t, rh = (2 * NN + 1) * RXH + t, rh2 = (2 * NN - 1) * RXH + t, rh3 = (2 * NN - 2) * RXH + t;
+                    mxz_r[rh] -= mxz_r[rh3];
+                    mzz_r[rh] -= mzz_r[rh2];
+                    mxz_r[rh1] -= mxz_r[rh2];
+                    mzz_r[rh1] = 0.f;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- pass A: own-cell transpose; nA..nD replace four of the split cotangents in the staged rects ----
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = R.r0 + j, gz = gz0 + j;
+            const int hb = (r + NN) * RXH + R.c0 + HX;
+            const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
+            float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) LS[f] = ld4(LSr + f * HQ + hb);
+            k2_cell<PML>(g, m, LS, ld4(MS + hb), ld4(mzz_r + hb), ld4(mxz_r + hb), C11[j], C13[j], C33[j], C55[j], PXN[j], PXI[j], PZN[j], PZI[j],
+                         l, q, nA, nB, nC, nD, N);
+            st4(LSr + hb, nA); st4(LSr + HQ + hb, nB); st4(LSr + 4 * HQ + hb, nC); st4(LSr + 5 * HQ + hb, nD);
+            G11[j] = add4(G11[j], mul4(q[0], D[0][j]));
+            G13[j] = add4(G13[j], add4(mul4(q[1], D[1][j]), mul4(q[2], D[0][j])));
+            G33[j] = add4(G33[j], mul4(q[3], D[1][j]));
+            G55[j] = add4(G55[j], add4(mul4(q[4], D[2][j]), mul4(q[5], D[3][j])));
+            if (col_ok && gz < g.nzp) {
+                float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LS + 6 * (a.lcur ^ 1)) * fp;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) st4(P + f * fp, N[f]);
+                if (a.g_src && m != 0u && s_sz[s - s_lo] == gz) {       // 3T
+                    const int dc = s_sx[s - s_lo] - gx;
+                    if (dc >= 0 && dc < 4 && ((m >> dc) & 1u)) {
+                        const float* M = a.mt + (size_t)s * 9;
+                        a.g_src[(size_t)s * g.nt + a.it] = -(M[0] / 2.0f) * (comp4(l[0], dc) + comp4(l[1], dc))
+                                                          - (M[8] / 2.0f) * (comp4(l[2], dc) + comp4(l[3], dc))
+                                                          - (M[2] / 2.0f) * (comp4(l[4], dc) + comp4(l[5], dc));
+                    }
+                }
+            }
+        }
+        for (int i = tid; i < G::NRING; i += NTH) {
+            int r, gi;
+            ring_cell<NN>(i, r, gi);
+            const int gzr = Z0 + r, gxr = X0 + 4 * gi;
+            const int hb = (r + NN) * RXH + 4 * gi + HX;
+            const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
+            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
+            float4 pxn = one4(), pxi = one4(), pzn = one4(), pzi = one4();
+            if (PML) {
+                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+                const float4 pxd = add4(one4(), smul(g.half_dt, bx_)), pzd = add4(one4(), smul(g.half_dt, bz_));
+                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
+                pxi = div4(one4(), pxd); pzi = div4(one4(), pzd);
+            }
+            float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) LS[f] = ld4(LSr + f * HQ + hb);
+            k2_cell<PML>(g, m, LS, ld4(MS + hb), ld4(mzz_r + hb), ld4(mxz_r + hb), ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol),
+                         ldk4(a.cp.c33 + o, pol), ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, l, q, nA, nB, nC, nD, N);
+            st4(LSr + hb, nA); st4(LSr + HQ + hb, nB); st4(LSr + 4 * HQ + hb, nC); st4(LSr + 5 * HQ + hb, nD);
+        }
+        __syncthreads();
+        // ---- pass B: 2T/1T gathers -> cotangents of the velocity sums (pre-step) --------------------
+        {
+            const float* NA = LSr; const float* NB = LSr + HQ; const float* NC = LSr + 4 * HQ; const float* ND = LSr + 5 * HQ;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = R.r0 + j, gz = gz0 + j;
+                const int hb = (r + NN) * RXH + R.c0 + HX;
+                float sa[12], sc[12];
+                ldseg(NA + hb, sa); ldseg(NC + hb, sc);
+                float4 wb[2 * NN], wd[2 * NN];
+#pragma unroll
+                for (int q = 0; q < 2 * NN; ++q) {
+                    wb[q] = ld4(NB + hb + (q - NN + 1) * RXH);      // (D-z)^T
+                    wd[q] = ld4(ND + hb + (q - NN) * RXH);          // (D+z)^T
+                }
+                const float4 nvx = add4(xgath<NN, 1>(sa, g.c), zgath<NN>(wd, g.c));
+                const float4 nvz = add4(zgath<NN>(wb, g.c), xgath<NN, 0>(sc, g.c));
+                if (col_ok && gz < g.nzp) {
+                    float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx;
+                    st4(P + P_LVX * fp, nvx); st4(P + P_LVZ * fp, nvz);
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (pc.valid) { if (tid == 0) k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int gz = gz0 + j;
+        if (col_ok && gz < g.nzp) {
+            float* gp = a.gpart + (size_t)chunk * 6 * g.plane + (size_t)gz * g.ld + gx;
+            red4(gp, G11[j]); red4(gp + g.plane, G13[j]); red4(gp + 2 * g.plane, G33[j]); red4(gp + 3 * g.plane, G55[j]);
+        }
+    }
+}
+
+template <int NN, bool FS>
+__global__ void __launch_bounds__(NTH, 2)
+elf_k2(const __grid_constant__ CUtensorMap th, const EGeom g, const K2Args a)
+{
+    using G = Geo<NN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = (uint64_t*)(smem + NSTAGE * G::K2_STAGE);
+    int* s_sz = (int*)(bar + 8);
+    int* s_sx = s_sz + CMAX;
+    const int tid = threadIdx.x;
+    if (tid == 0) { for (int k = 0; k < NSTAGE; ++k) mbar_init(bar + k, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    int stage = 0;
+    const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    Cursor pc;
+    pc.set(blockIdx.x, g, a.w);
+    griddep_launch_dependents();
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
+        const int s_lo = a.w.s_begin + chunk * a.w.chunk;
+        const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
+        const bool first = item == (int)blockIdx.x;
+        if (a.tflags[tile]) k2_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                k2_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        __syncthreads();
+    }
+}
+
+// ---- set-up kernels ------------------------------------------------------------------------------
+// coefficient pack: eight planes [cprows][cpld] (C11,C13,C33,C55,bx,bz,bcx,bcz), logical cell (z,x) at
+// [(z+CPZ)*cpld + x+CPX], zero outside the grid
+struct PackSrc { const float* p[8]; };
+__global__ void elf_pack_coefs(int nzp, int nxp, int cprows, int cpld, size_t cpplane, PackSrc src, float* __restrict__ pack)
+{
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x, zz = blockIdx.y;
+    if (xx >= cpld || zz >= cprows) return;
+    const int x = xx - CPX, z = zz - CPZ;
+    const bool in = (z >= 0) && (z < nzp) && (x >= 0) && (x < nxp);
+    const size_t c = in ? (size_t)z * nxp + x : 0;
+    const size_t o = (size_t)zz * cpld + xx;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pack[k * cpplane + o] = in ? src.p[k][c] : 0.f;
+}
+// tile flag = 1 when any cell of the tile's neighbourhood (tile + apron) has a non-zero PML profile
+__global__ void elf_tile_flags(int ntx, int cpld, size_t cpplane, const float* __restrict__ pack, unsigned char* __restrict__ flags)
+{
+    const int tile = blockIdx.x;
+    const int tzi = tile / ntx, txi = tile - tzi * ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int W = TX + 2 * CPX, H = TZ + 2 * CPZ;
+    int bad = 0;
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
+        const size_t o = (size_t)(Z0 + i / W) * cpld + (X0 + i % W);
+        if (pack[6 * cpplane + o] != 0.f || pack[7 * cpplane + o] != 0.f) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flags[tile] = (unsigned char)(bad ? 1 : 0);
+}
+// receiver buckets: counting sort of the receivers by tile
+__device__ __forceinline__ int rcv_tile(int nzp, int nxp, int ntx, int64_t z, int64_t x)
+{
+    if (z < 0 || z >= nzp || x < 0 || x >= nxp) return -1;
+    return (int)z / TZ * ntx + (int)x / TX;
+}
+__global__ void elf_rcv_count(int nzp, int nxp, int ntx, int nr, const int64_t* __restrict__ rx, const int64_t* __restrict__ rz, int* __restrict__ cnt)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nr) return;
+    const int t = rcv_tile(nzp, nxp, ntx, rz[r], rx[r]);
+    if (t >= 0) atomicAdd(cnt + t, 1);
+}
+__global__ void elf_rcv_scan(int ntiles, const int* __restrict__ cnt, int* __restrict__ start, int* __restrict__ cursor)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int acc = 0;
+        for (int t = 0; t < ntiles; ++t) { start[t] = acc; cursor[t] = acc; acc += cnt[t]; }
+        start[ntiles] = acc;
+    }
+}
+__global__ void elf_rcv_fill(int nzp, int nxp, int ntx, int nr, const int64_t* __restrict__ rx, const int64_t* __restrict__ rz,
+                             int* __restrict__ cursor, int* __restrict__ id, int* __restrict__ zx)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nr) return;
+    const int t = rcv_tile(nzp, nxp, ntx, rz[r], rx[r]);
+    if (t < 0) return;
+    const int i = atomicAdd(cursor + t, 1);
+    id[i] = r;
+    zx[i] = ((int)rz[r] << 16) | (int)rx[r];
+}
+__global__ void elf_rcv_nbr(int ntx, int ntz, const int* __restrict__ start, unsigned char* __restrict__ nbr)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntx * ntz) return;
+    const int tz = t / ntx, tx = t - tz * ntx;
+    int any = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int z2 = tz + dz, x2 = tx + dx;
+            if (z2 < 0 || z2 >= ntz || x2 < 0 || x2 >= ntx) continue;
+            const int t2 = z2 * ntx + x2;
+            any |= (start[t2 + 1] > start[t2]);
+        }
+    nbr[t] = (unsigned char)any;
+}
+// pitched partial planes -> dense caller planes
+__global__ void elf_reduce_parts(int nzp, int nxp, int ld, size_t plane, int nparts, int k, const float* __restrict__ part, float* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= nxp || z >= nzp) return;
+    float acc = 0.f;
+    for (int p = 0; p < nparts; ++p) acc += part[((size_t)p * 6 + k) * plane + (size_t)z * ld + x];
+    out[(size_t)z * nxp + x] = acc;
+}
+
+// squares of the five sum fields of the current state, summed over shots (:414-418), physical cells only
+__global__ void elf_illum_acc(EGeom g, int NN, int nz, int nx, int nabc, int zoff, int sb, int se, const float* __restrict__ planes, float* __restrict__ ill)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= nx || z >= nz) return;
+    const int gz = z + zoff, gxx = x + nabc;
+    const size_t c = (size_t)gz * g.ld + gxx, o = (size_t)z * nx + x, n = (size_t)nz * nx;
+    const size_t fp = (size_t)g.ns * g.plane;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = sb; s < se; ++s) {
+        const float* P = planes + (size_t)s * g.plane + c;
+        float txx = P[P_TXX * fp], tzz = P[P_TZZ * fp], txz = P[P_TXZ * fp];
+        if (g.fs && gz == NN) tzz = 0.f;                        // tzz[h-1] = 0 (:380)
+        const float vx = P[P_VXX * fp] + P[P_VXZ * fp], vz = P[P_VZX * fp] + P[P_VZZ * fp];
+        acc[0] += txx * txx; acc[1] += tzz * tzz; acc[2] += txz * txz; acc[3] += vx * vx; acc[4] += vz * vz;
+    }
+    for (int k = 0; k < 5; ++k) ill[k * n + o] += acc[k];
+}
+__global__ void elf_illum_out(int n, const float* __restrict__ ill, float* o0, float* o1, float* o2, float* o3, float* o4)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* out[5] = {o0, o1, o2, o3, o4};
+    for (int k = 0; k < 5; ++k) if (out[k]) out[k][i] = ill[(size_t)k * n + i];
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+constexpr int CTAS_PER_SM = 2;
+
+int elf_num_sms()
+{
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+struct EFPlan {
+    EGeom g;
+    int ns, nr, NN, FS, save, n_segments, nz, nx, nabc, zoff;
+    int K, nseg, nckpt, G;
+    int chunk, nchunks;
+    int cprows; size_t cpplane;
+    float* pack; unsigned char* tflags;
+    float* planes; int nfields;
+    float *hist, *ckpt, *gpart, *ill;
+    int *rcv_cnt, *rcv_start, *rcv_cursor, *rcv_id, *rcv_zx; unsigned char* rcv_nbr;
+    size_t bytes;
+};
+
+int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
+{
+    EGeom& g = P->g;
+    const int NN = d->fd_order / 2;
+    g.nzp = d->nzp; g.nxp = d->nxp; g.ld = (d->nxp + 31) / 32 * 32; g.fs = d->free_surface ? 1 : 0; g.nt = d->nt; g.ns = d->ns;
+    g.ntx = cdiv(g.nxp, TX); g.ntz = cdiv(g.nzp, TZ);
+    g.cpld = g.ntx * TX + 2 * CPX;
+    g.plane = (size_t)g.nzp * g.ld;
+    g.dt = d->dt; g.dx = d->dx; g.dz = d->dz; g.dt_dx = d->dt_dx; g.dt_dz = d->dt_dz; g.half_dt = d->half_dt;
+    g.rdx = 1.0f / d->dx; g.rdz = 1.0f / d->dz;
+    for (int k = 0; k < 3; ++k) g.c[k] = d->fdc[k];
+    P->cprows = g.ntz * TZ + 2 * CPZ;
+    P->cpplane = align_up((size_t)P->cprows * g.cpld, 64);
+    P->ns = d->ns; P->nr = d->nr; P->NN = NN; P->FS = g.fs; P->save = d->save_history ? 1 : 0;
+    P->n_segments = d->n_segments > 0 ? d->n_segments : 1;
+    P->nz = d->nz; P->nx = d->nx; P->nabc = d->nabc; P->zoff = d->free_surface ? NN : NN + d->nabc;
+    int K = d->ckpt_interval;
+    if (K <= 0 || K >= d->nt) K = d->nt;
+    P->K = K; P->nseg = cdiv(d->nt, K); P->nckpt = P->nseg > 2 ? P->nseg - 2 : 0;
+    int G = d->shots_per_group;
+    if (G <= 0 || G > d->ns) G = d->ns;
+    P->G = G;
+    const int ntiles = g.ntx * g.ntz;
+    int nchunks = d->reserved[1] > 0 ? cdiv(G, d->reserved[1]) : (6 * CTAS_PER_SM * nsm + ntiles - 1) / ntiles;    // >= ~6 rounds over the resident CTAs
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > G) nchunks = G;
+    int chunk = cdiv(G, nchunks);
+    if (chunk > CMAX) chunk = CMAX;
+    P->chunk = chunk; P->nchunks = cdiv(G, chunk);
+    Carver cv(ws);
+    const size_t sp = (size_t)d->ns * g.plane;
+    P->pack = cv.take<float>(8 * P->cpplane);
+    P->tflags = cv.take<unsigned char>(ntiles);
+    P->nfields = P->save ? P_COUNT : P_FWD_COUNT;
+    P->planes = cv.take<float>((size_t)P->nfields * sp);
+    P->ill = cv.take<float>((size_t)5 * d->nz * d->nx);
+    P->rcv_cnt = cv.take<int>(ntiles + 1); P->rcv_start = cv.take<int>(ntiles + 1); P->rcv_cursor = cv.take<int>(ntiles + 1);
+    P->rcv_id = cv.take<int>(d->nr > 0 ? d->nr : 1); P->rcv_zx = cv.take<int>(d->nr > 0 ? d->nr : 1);
+    P->rcv_nbr = cv.take<unsigned char>(ntiles);
+    P->hist = P->ckpt = P->gpart = nullptr;
+    if (P->save) {
+        P->gpart = cv.take<float>((size_t)P->nchunks * 6 * g.plane);
+        if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * 10 * sp);
+        P->hist = cv.take<float>((size_t)K * NHIST * sp);
+    }
+    P->bytes = cv.off;
+    return ADFWI_OK;
+}
+
+ECoef elf_pack_ptrs(const EFPlan& P)
+{
+    const size_t o = (size_t)CPZ * P.g.cpld + CPX;
+    ECoef c;
+    c.c11 = P.pack + 0 * P.cpplane + o; c.c13 = P.pack + 1 * P.cpplane + o; c.c33 = P.pack + 2 * P.cpplane + o; c.c55 = P.pack + 3 * P.cpplane + o;
+    c.bx = P.pack + 4 * P.cpplane + o; c.bz = P.pack + 5 * P.cpplane + o; c.bcx = P.pack + 6 * P.cpplane + o; c.bcz = P.pack + 7 * P.cpplane + o;
+    return c;
+}
+RcvB elf_bucket_ptrs(const EFPlan& P) { RcvB b; b.start = P.rcv_start; b.id = P.rcv_id; b.zx = P.rcv_zx; b.nbr = P.rcv_nbr; return b; }
+
+int elf_setup(const EFPlan& P, cudaStream_t st, const float* const* coef, const float* bcx, const float* bcz, const int64_t* rx, const int64_t* rz)
+{
+    const EGeom& g = P.g;
+    PackSrc src;
+    for (int k = 0; k < 6; ++k) src.p[k] = coef[k];
+    src.p[6] = bcx; src.p[7] = bcz;
+    elf_pack_coefs<<<dim3(cdiv(g.cpld, 128), P.cprows), 128, 0, st>>>(g.nzp, g.nxp, P.cprows, g.cpld, P.cpplane, src, P.pack);
+    ADFWI_LAUNCH_CHECK();
+    const int ntiles = g.ntx * g.ntz;
+    elf_tile_flags<<<ntiles, 128, 0, st>>>(g.ntx, g.cpld, P.cpplane, P.pack, P.tflags);
+    ADFWI_LAUNCH_CHECK();
+    ADFWI_CUDA(cudaMemsetAsync(P.rcv_cnt, 0, sizeof(int) * (ntiles + 1), st));
+    if (P.nr > 0) {
+        elf_rcv_count<<<cdiv(P.nr, 128), 128, 0, st>>>(g.nzp, g.nxp, g.ntx, P.nr, rx, rz, P.rcv_cnt);
+        ADFWI_LAUNCH_CHECK();
+    }
+    elf_rcv_scan<<<1, 32, 0, st>>>(ntiles, P.rcv_cnt, P.rcv_start, P.rcv_cursor);
+    ADFWI_LAUNCH_CHECK();
+    if (P.nr > 0) {
+        elf_rcv_fill<<<cdiv(P.nr, 128), 128, 0, st>>>(g.nzp, g.nxp, g.ntx, P.nr, rx, rz, P.rcv_cursor, P.rcv_id, P.rcv_zx);
+        ADFWI_LAUNCH_CHECK();
+    }
+    elf_rcv_nbr<<<cdiv(ntiles, 128), 128, 0, st>>>(g.ntx, g.ntz, P.rcv_start, P.rcv_nbr);
+    ADFWI_LAUNCH_CHECK();
+    return ADFWI_OK;
+}
+
+struct EMaps { CUtensorMap halo, core; };
+
+int elf_make_maps(const EFPlan& P, EMaps* M)
+{
+    const EGeom& g = P.g;
+    int rc = make_tmap_f32(&M->halo, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, RXH, TZ + 2 * P.NN);
+    if (rc) return rc;
+    return make_tmap_f32(&M->core, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, TX, TZ);
+}
+
+template <typename Kern, typename... Args>
+cudaError_t elf_launch(Kern kern, int grid, int smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+inline bool elf_use_pdl()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+template <typename K> int elf_set_smem(K kern, int bytes) { return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
+template <int NN> constexpr int s_smem() { return NSTAGE * Geo<NN>::S_STAGE + TAIL_BYTES; }
+template <int NN> constexpr int v_smem() { return NSTAGE * Geo<NN>::V_STAGE + TAIL_SMALL; }
+template <int NN> constexpr int k1_smem() { return NSTAGE * Geo<NN>::K1_STAGE + TAIL_SMALL; }
+template <int NN> constexpr int k2_smem() { return NSTAGE * Geo<NN>::K2_STAGE + TAIL_SMALL; }
+static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472, "two CTAs per SM must fit in shared memory");
+
+template <int NN> int elf_init_kernels()
+{
+    static bool done = false;
+    if (done) return 0;
+    int rc = 0;
+    rc |= elf_set_smem(elf_s<NN, true, true>, s_smem<NN>());   rc |= elf_set_smem(elf_s<NN, true, false>, s_smem<NN>());
+    rc |= elf_set_smem(elf_s<NN, false, true>, s_smem<NN>());  rc |= elf_set_smem(elf_s<NN, false, false>, s_smem<NN>());
+    rc |= elf_set_smem(elf_v<NN, true, true>, v_smem<NN>());   rc |= elf_set_smem(elf_v<NN, true, false>, v_smem<NN>());
+    rc |= elf_set_smem(elf_v<NN, false, true>, v_smem<NN>());  rc |= elf_set_smem(elf_v<NN, false, false>, v_smem<NN>());
+    rc |= elf_set_smem(elf_k1<NN, true>, k1_smem<NN>());       rc |= elf_set_smem(elf_k1<NN, false>, k1_smem<NN>());
+    rc |= elf_set_smem(elf_k2<NN, true>, k2_smem<NN>());       rc |= elf_set_smem(elf_k2<NN, false>, k2_smem<NN>());
+    if (!rc) done = true;
+    return rc;
+}
+
+inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid)
+{
+    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = P.chunk; w.nchunks = cdiv(se - sb, P.chunk);
+    const int nitems = P.g.ntx * P.g.ntz * w.nchunks;
+    const int cap = CTAS_PER_SM * elf_num_sms();
+    *grid = nitems < cap ? nitems : cap;
+    return w;
+}
+
+struct EArgs { const float *mt, *src_v; const int64_t *sx, *sz; };
+
+// one forward step of shots [sb,se): elf_s then elf_v
+template <int NN>
+int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, int se, int it, bool save, int tl,
+                     const EArgs& ea, float* const* rcv)
+{
+    const EGeom& g = P.g;
+    int grid;
+    const Walk w = elf_walk(P, sb, se, &grid);
+    const bool pdl = elf_use_pdl();
+    {
+        SArgs a;
+        a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.mt = ea.mt; a.src_v = ea.src_v; a.sx = ea.sx; a.sz = ea.sz;
+        a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it; a.w = w;
+        TimedLaunch tl_(KC_EL_FWD_STRESS, st);
+        if (P.FS) { if (save) ADFWI_CUDA(elf_launch(elf_s<NN, true, true>, grid, s_smem<NN>(), st, pdl, M.halo, M.core, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_s<NN, true, false>, grid, s_smem<NN>(), st, pdl, M.halo, M.core, g, a)); }
+        else      { if (save) ADFWI_CUDA(elf_launch(elf_s<NN, false, true>, grid, s_smem<NN>(), st, pdl, M.halo, M.core, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_s<NN, false, false>, grid, s_smem<NN>(), st, pdl, M.halo, M.core, g, a)); }
+    }
+    ADFWI_LAUNCH_CHECK();
+    {
+        VArgs a;
+        a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it;
+        a.nr = rcv ? P.nr : 0; a.rb = elf_bucket_ptrs(P);
+        for (int k = 0; k < 5; ++k) a.rcv[k] = rcv ? rcv[k] : nullptr;
+        a.w = w;
+        TimedLaunch tl_(KC_EL_FWD_VEL, st);
+        if (P.FS) { if (save) ADFWI_CUDA(elf_launch(elf_v<NN, true, true>, grid, v_smem<NN>(), st, pdl, M.halo, M.core, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_v<NN, true, false>, grid, v_smem<NN>(), st, pdl, M.halo, M.core, g, a)); }
+        else      { if (save) ADFWI_CUDA(elf_launch(elf_v<NN, false, true>, grid, v_smem<NN>(), st, pdl, M.halo, M.core, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_v<NN, false, false>, grid, v_smem<NN>(), st, pdl, M.halo, M.core, g, a)); }
+    }
+    ADFWI_LAUNCH_CHECK();
+    return ADFWI_OK;
+}
+
+// the 10 persistent split fields of shots [sb,se) <-> checkpoint slot
+int elf_copy_state(const EFPlan& P, cudaStream_t st, int sb, int se, float* ck, bool to_ckpt)
+{
+    const size_t sp = (size_t)P.ns * P.g.plane;
+    const size_t off = (size_t)sb * P.g.plane, cnt = (size_t)(se - sb) * P.g.plane * sizeof(float);
+    for (int f = 0; f < 10; ++f) {
+        float* a = P.planes + (size_t)f * sp + off;
+        float* b = ck + (size_t)f * sp + off;
+        ADFWI_CUDA(cudaMemcpyAsync(to_ckpt ? b : a, to_ckpt ? a : b, cnt, cudaMemcpyDeviceToDevice, st));
+    }
+    return ADFWI_OK;
+}
+int elf_zero_fields(const EFPlan& P, cudaStream_t st, int f0, int f1, int sb, int se)
+{
+    const size_t sp = (size_t)P.ns * P.g.plane;
+    if (sb == 0 && se == P.ns) return (int)cudaMemsetAsync(P.planes + (size_t)f0 * sp, 0, (size_t)(f1 - f0) * sp * sizeof(float), st);
+    for (int f = f0; f < f1; ++f)
+        ADFWI_CUDA(cudaMemsetAsync(P.planes + (size_t)f * sp + (size_t)sb * P.g.plane, 0, (size_t)(se - sb) * P.g.plane * sizeof(float), st));
+    return ADFWI_OK;
+}
+
+template <int NN>
+int elf_forward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs& ea, float* const* rcv, float* const* illum)
+{
+    const EGeom& g = P.g;
+    const int nt = g.nt;
+    const int csz = cdiv(nt, P.n_segments);
+    const int nphys = P.nz * P.nx;
+    if (illum) ADFWI_CUDA(cudaMemsetAsync(P.ill, 0, sizeof(float) * 5 * nphys, st));
+    for (int sb = 0; sb < P.ns; sb += P.G) {
+        const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
+        int rc = elf_zero_fields(P, st, 0, P_FWD_COUNT, sb, se);
+        if (rc) return rc;
+        for (int it = 0; it < nt; ++it) {
+            const int seg = it / P.K, tl = it - seg * P.K;
+            if (P.save && tl == 0 && seg >= 1 && seg <= P.nseg - 2) {
+                rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, true);
+                if (rc) return rc;
+            }
+            const bool save = P.save && seg == P.nseg - 1;
+            rc = elf_forward_step<NN>(P, M, st, sb, se, it, save, tl, ea, P.nr > 0 ? rcv : nullptr);
+            if (rc) return rc;
+            if (illum && ((it + 1) % csz == 0 || it == nt - 1)) {
+                elf_illum_acc<<<dim3(cdiv(P.nx, 128), P.nz), 128, 0, st>>>(g, NN, P.nz, P.nx, P.nabc, P.zoff, sb, se, P.planes, P.ill);
+                ADFWI_LAUNCH_CHECK();
+            }
+        }
+    }
+    if (illum) {
+        elf_illum_out<<<cdiv(nphys, 256), 256, 0, st>>>(nphys, P.ill, illum[0], illum[1], illum[2], illum[3], illum[4]);
+        ADFWI_LAUNCH_CHECK();
+    }
+    return ADFWI_OK;
+}
+
+template <int NN>
+int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs& ea, const float* const* g_rcv, float* const* g_coef, float* g_src)
+{
+    const EGeom& g = P.g;
+    const int nt = g.nt;
+    const bool pdl = elf_use_pdl();
+    ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks * 6 * g.plane, st));
+    for (int sb = 0; sb < P.ns; sb += P.G) {
+        const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
+        int rc = elf_zero_fields(P, st, P_LV, P_COUNT, sb, se);
+        if (rc) return rc;
+        int grid;
+        const Walk w = elf_walk(P, sb, se, &grid);
+        int lcur = 0;
+        for (int seg = P.nseg - 1; seg >= 0; --seg) {
+            const int t0 = seg * P.K, t1 = t0 + P.K < nt ? t0 + P.K : nt;
+            if (seg != P.nseg - 1) {
+                if (seg == 0) rc = elf_zero_fields(P, st, 0, P_FWD_COUNT, sb, se);
+                else          rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, false);
+                if (rc) return rc;
+                for (int it = t0; it < t1; ++it) {
+                    rc = elf_forward_step<NN>(P, M, st, sb, se, it, true, it - t0, ea, nullptr);
+                    if (rc) return rc;
+                }
+            }
+            for (int it = t1 - 1; it >= t0; --it) {
+                {
+                    K1Args a;
+                    a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
+                    a.nr = P.nr; a.rb = elf_bucket_ptrs(P);
+                    for (int k = 0; k < 5; ++k) a.g[k] = g_rcv[k];
+                    a.gpart = P.gpart; a.w = w;
+                    TimedLaunch tl_(KC_EL_ADJ_VEL, st);
+                    if (P.FS) ADFWI_CUDA(elf_launch(elf_k1<NN, true>, grid, k1_smem<NN>(), st, pdl, M.halo, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_k1<NN, false>, grid, k1_smem<NN>(), st, pdl, M.halo, g, a));
+                }
+                ADFWI_LAUNCH_CHECK();
+                {
+                    K2Args a;
+                    a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
+                    a.mt = ea.mt; a.sx = ea.sx; a.sz = ea.sz; a.g_src = g_src; a.gpart = P.gpart; a.w = w;
+                    TimedLaunch tl_(KC_EL_ADJ_STRESS, st);
+                    if (P.FS) ADFWI_CUDA(elf_launch(elf_k2<NN, true>, grid, k2_smem<NN>(), st, pdl, M.halo, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_k2<NN, false>, grid, k2_smem<NN>(), st, pdl, M.halo, g, a));
+                }
+                ADFWI_LAUNCH_CHECK();
+                lcur ^= 1;
+            }
+        }
+    }
+    for (int k = 0; k < 6; ++k) {
+        elf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.plane, P.nchunks, k, P.gpart, g_coef[k]);
+        ADFWI_LAUNCH_CHECK();
+    }
+    return ADFWI_OK;
+}
+
+}  // namespace
+
+bool elf_supported(const adfwi_elastic_desc* d)
+{
+    if (!d || !d->abc_pml) return false;
+    if (d->fd_order != 4 && d->fd_order != 6) return false;
+    if (d->reserved[0] & 1) return false;
+    if (d->nzp >= 32768 || d->nxp >= 65536) return false;      // receiver cells are packed as (z<<16)|x
+    if ((uint64_t)P_COUNT * (uint64_t)d->ns >= (1ull << 31)) return false;
+    return true;
+}
+
+size_t elf_workspace_bytes(const adfwi_elastic_desc* d)
+{
+    EFPlan P;
+    elf_make_plan(d, nullptr, &P, 148);
+    return P.bytes;
+}
+
+int elf_forward(const adfwi_elastic_desc* d, const float* const* coef, const float* bcx, const float* bcz, const float* mt,
+                const float* src_v, const int64_t* sx, const int64_t* sz, const int64_t* rx, const int64_t* rz,
+                float* const* rcv, float* const* illum, void* ws, cudaStream_t st)
+{
+    EFPlan P;
+    elf_make_plan(d, ws, &P, 148);
+    int rc = P.NN == 2 ? elf_init_kernels<2>() : elf_init_kernels<3>();
+    if (rc) return rc;
+    EMaps M;
+    rc = elf_make_maps(P, &M);
+    if (rc) return rc;
+    rc = elf_setup(P, st, coef, bcx, bcz, rx, rz);
+    if (rc) return rc;
+    EArgs ea; ea.mt = mt; ea.src_v = src_v; ea.sx = sx; ea.sz = sz;
+    return P.NN == 2 ? elf_forward_t<2>(P, M, st, ea, rcv, illum) : elf_forward_t<3>(P, M, st, ea, rcv, illum);
+}
+
+int elf_backward(const adfwi_elastic_desc* d, const float* const* coef, const float* bcx, const float* bcz, const float* mt,
+                 const float* src_v, const int64_t* sx, const int64_t* sz, const int64_t* rx, const int64_t* rz,
+                 const float* const* g_rcv, float* const* g_coef, float* g_src, void* ws, cudaStream_t st)
+{
+    (void)coef; (void)bcx; (void)bcz; (void)rx; (void)rz;      // pack, tile flags and receiver buckets were left in the workspace by forward
+    EFPlan P;
+    elf_make_plan(d, ws, &P, 148);
+    int rc = P.NN == 2 ? elf_init_kernels<2>() : elf_init_kernels<3>();
+    if (rc) return rc;
+    EMaps M;
+    rc = elf_make_maps(P, &M);
+    if (rc) return rc;
+    EArgs ea; ea.mt = mt; ea.src_v = src_v; ea.sx = sx; ea.sz = sz;
+    return P.NN == 2 ? elf_backward_t<2>(P, M, st, ea, g_rcv, g_coef, g_src) : elf_backward_t<3>(P, M, st, ea, g_rcv, g_coef, g_src);
+}
+
+}  // namespace adfwi
+#endif  // !ADFWI_HOST_EMUL

@@ -87,6 +87,8 @@ class ElasticFD(torch.autograd.Function):
         save = any(need)
         desc = make_desc(nzp, nxp, ns, nt, nr, nz, nx, nabc, free_surface, fd_order, abc_pml, dt, dx, dz,
                          n_segments, save, 0, config["shots_per_group"])
+        desc.reserved[0] = 1 if config["force_generic"] else 0
+        desc.reserved[1] = int(config.get("shots_per_chunk", 0))
         with torch.cuda.device(dev):
             if save and config["ckpt_interval"] is None:
                 free_b, _ = torch.cuda.mem_get_info(dev)

@@ -7,7 +7,8 @@ out = open(os.path.join(root, "profiles", f"{tag}_summary.md"), "w")
 lf = os.path.join(root, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(lf):
     rows = [r for r in csv.reader(open(lf)) if len(r) > 5]
-    hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = next((i for i, r in enumerate(rows) if "Kernel Name" in r), None)
+if os.path.exists(lf) and hdr is not None:
     H = rows[hdr]; kn, mv = H.index("Kernel Name"), H.index("Metric Value")
     agg = collections.OrderedDict()
     for r in rows[hdr + 1:]:
