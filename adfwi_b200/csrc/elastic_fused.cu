@@ -39,7 +39,8 @@ constexpr int TX = 64, TZ = 16;             // tile interior
 constexpr int HX = 4;                       // x halo of the staged rectangles (one float4 group)
 constexpr int RXH = TX + 2 * HX;            // 72 floats per halo row
 constexpr int NG = TX / 4;                  // float4 groups per tile row
-constexpr int NTH = NG * (TZ / 2);          // 128 threads: float4 x 2 rows each
+constexpr int RPT = 2;                      // tile rows per thread
+constexpr int NTH = NG * (TZ / RPT);        // threads per CTA: one float4 group x RPT rows each
 constexpr int CMAX = 32;                    // max shots per chunk
 constexpr int CPX = 4, CPZ = 4;             // apron of the coefficient pack
 constexpr int NSTAGE = 2;
@@ -134,8 +135,8 @@ __device__ __forceinline__ float4 divs(const float4& a, float s) { return make_f
 // so the second one returns RN(a/b) (Markstein's theorem) -- the same bits as the IEEE division of the eager
 // reference -- at 5 instructions and with no slow path for zero numerators (the compiler's division sequence
 // takes its out-of-line path for every zero operand, i.e. for every cell the wave has not reached yet).
-// The remainders are exact only away from the underflow / overflow range: numerators with an exponent outside
-// [2^-60, 2^60] (other than zero) take the IEEE division.  Divisors are grid spacings and 1 + dt/2*profile.
+// The remainders are exact only away from the underflow range: non-zero numerators below 2^-100 in magnitude
+// take the IEEE division (DivGuard).  Divisors are grid spacings and 1 + dt/2*profile (moderate magnitudes).
 __device__ __forceinline__ float fdiv1(float a, float b, float rb)
 {
     float q = a * rb;
@@ -143,23 +144,32 @@ __device__ __forceinline__ float fdiv1(float a, float b, float rb)
     q = __fmaf_rn(__fmaf_rn(-b, q, a), rb, q);
     return q;
 }
-__device__ __forceinline__ bool div_safe1(float a)
+// guard accumulator: ok() is true when every numerator added is zero or at least 2^-100 in magnitude
+// (t = 2*bits - 1 wraps zero to the top of the unsigned range; one IADD3 + one unsigned min per value)
+struct DivGuard {
+    unsigned mn;
+    __device__ __forceinline__ DivGuard() : mn(0xffffffffu) {}
+    __device__ __forceinline__ void add(const float4& a)
+    {
+        const unsigned t0 = 2u * __float_as_uint(a.x) - 1u, t1 = 2u * __float_as_uint(a.y) - 1u;
+        const unsigned t2 = 2u * __float_as_uint(a.z) - 1u, t3 = 2u * __float_as_uint(a.w) - 1u;
+        mn = min(min(mn, min(t0, t1)), min(t2, t3));
+    }
+    __device__ __forceinline__ bool ok() const { return mn >= ((27u << 24) - 1u); }
+};
+__device__ __noinline__ float4 ieee_div4(float4 a, float4 b)      // rare path, kept out of line (code size)
 {
-    const unsigned u = __float_as_uint(a) << 1;
-    return (u - (67u << 24) < (121u << 24)) || u == 0u;
+    return make_float4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w);
 }
-__device__ __forceinline__ bool div_safe4(const float4& a) { return div_safe1(a.x) && div_safe1(a.y) && div_safe1(a.z) && div_safe1(a.w); }
+__device__ __forceinline__ float4 ieee_divs(const float4& a, float b) { return ieee_div4(a, make_float4(b, b, b, b)); }
+// unguarded fast divisions: the caller adds the numerator to a DivGuard and redoes the work with ieee_div4 when !ok()
 __device__ __forceinline__ float4 fdiv4(const float4& a, const float4& b, const float4& rb)
 {
-    float4 q = make_float4(fdiv1(a.x, b.x, rb.x), fdiv1(a.y, b.y, rb.y), fdiv1(a.z, b.z, rb.z), fdiv1(a.w, b.w, rb.w));
-    if (!div_safe4(a)) q = make_float4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w);
-    return q;
+    return make_float4(fdiv1(a.x, b.x, rb.x), fdiv1(a.y, b.y, rb.y), fdiv1(a.z, b.z, rb.z), fdiv1(a.w, b.w, rb.w));
 }
 __device__ __forceinline__ float4 fdivs(const float4& a, float b, float rb)
 {
-    float4 q = make_float4(fdiv1(a.x, b, rb), fdiv1(a.y, b, rb), fdiv1(a.z, b, rb), fdiv1(a.w, b, rb));
-    if (!div_safe4(a)) q = make_float4(a.x / b, a.y / b, a.z / b, a.w / b);
-    return q;
+    return make_float4(fdiv1(a.x, b, rb), fdiv1(a.y, b, rb), fdiv1(a.z, b, rb), fdiv1(a.w, b, rb));
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 one4() { return make_float4(1.f, 1.f, 1.f, 1.f); }
@@ -252,7 +262,7 @@ struct Cursor {
 // thread roles: float4 group l, rows 2q and 2q+1 of the tile
 struct Roles {
     int q, l, r0, c0;
-    __device__ __forceinline__ explicit Roles(int tid) { q = tid / NG; l = tid - q * NG; r0 = 2 * q; c0 = 4 * l; }
+    __device__ __forceinline__ explicit Roles(int tid) { q = tid / NG; l = tid - q * NG; r0 = RPT * q; c0 = 4 * l; }
 };
 // ring float4 group i in [0, NRING): rows [-NN,0) and [TZ,TZ+NN) x groups [-1,NG], rows [0,TZ) x groups {-1,NG}
 template <int NN> __device__ __forceinline__ void ring_cell(int i, int& r, int& gi)
@@ -310,9 +320,9 @@ __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap*
         s_sz[tid] = (int)a.sz[s]; s_sx[tid] = (int)a.sx[s];
         s_sxx[tid] = (-(M[0] / 2.0f)) * v; s_szz[tid] = (-(M[8] / 2.0f)) * v; s_sxz[tid] = (-(M[2] / 2.0f)) * v;
     }
-    float4 C11[2], C13[2], C33[2], C55[2], PXN[2], PXI[2], PZN[2], PZI[2];
+    float4 C11[RPT], C13[RPT], C33[RPT], C55[RPT], PXN[RPT], PXI[RPT], PZN[RPT], PZI[RPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPT; ++j) {
         const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
         C11[j] = ldk4(a.cp.c11 + o, pol); C13[j] = ldk4(a.cp.c13 + o, pol);
         C33[j] = ldk4(a.cp.c33 + o, pol); C55[j] = ldk4(a.cp.c55 + o, pol);
@@ -360,7 +370,7 @@ __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap*
         }
         const bool has_src = (szs >= Z0) && (szs < Z0 + TZ) && (sxs >= X0) && (sxs < X0 + TX);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const int r = R.r0 + j, gz = gz0 + j;
             const int hb = (r + NN) * RXH + R.c0 + HX;
             float sx_[12], sz_[12];
@@ -487,9 +497,9 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
     const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
     const unsigned cm = col_mask<NN>(gx, g.nxp);
     const bool col_ok = gx < g.ld;
-    float4 DBX[2], DBZ[2], PXN[2], PXD[2], PZN[2], PZD[2], RPXD[2], RPZD[2];
+    float4 DBX[RPT], DBZ[RPT], PXN[RPT], PXD[RPT], PZN[RPT], PZD[RPT], RPXD[RPT], RPZD[RPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPT; ++j) {
         const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
         DBX[j] = smul(g.dt, ldk4(a.cp.bx + o, pol)); DBZ[j] = smul(g.dt, ldk4(a.cp.bz + o, pol));     // dt*bx, dt*bz (:387-394)
         if (PML) {
@@ -528,9 +538,9 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
             }
             __syncthreads();
         }
-        float4 nvx[2], nvz[2];
+        float4 nvx[RPT], nvz[RPT];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const int r = R.r0 + j, gz = gz0 + j;
             const int hb = (r + NN) * RXH + R.c0 + HX;
             float sxx_[12], sxz_[12];
@@ -548,16 +558,28 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
             float4 q0 = ld4(cv + co), q1 = ld4(cv + CF + co), q2 = ld4(cv + 2 * CF + co), q3 = ld4(cv + 3 * CF + co);
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
             float4 n0, n1, n2, n3;
-            if (PML) {
-                n0 = fdiv4(add4(mul4(PXN[j], q0), fdivs(mul4(DBX[j], dxf_txx), g.dx, g.rdx)), PXD[j], RPXD[j]);
-                n1 = fdiv4(add4(mul4(PZN[j], q1), fdivs(mul4(DBX[j], dzb_txz), g.dz, g.rdz)), PZD[j], RPZD[j]);
-                n2 = fdiv4(add4(mul4(PXN[j], q2), fdivs(mul4(DBZ[j], dxb_txz), g.dx, g.rdx)), PXD[j], RPXD[j]);
-                n3 = fdiv4(add4(mul4(PZN[j], q3), fdivs(mul4(DBZ[j], dzf_tzz), g.dz, g.rdz)), PZD[j], RPZD[j]);
-            } else {
-                n0 = add4(q0, fdivs(mul4(DBX[j], dxf_txx), g.dx, g.rdx));
-                n1 = add4(q1, fdivs(mul4(DBX[j], dzb_txz), g.dz, g.rdz));
-                n2 = add4(q2, fdivs(mul4(DBZ[j], dxb_txz), g.dx, g.rdx));
-                n3 = add4(q3, fdivs(mul4(DBZ[j], dzf_tzz), g.dz, g.rdz));
+            {
+                const float4 A0 = mul4(DBX[j], dxf_txx), A1 = mul4(DBX[j], dzb_txz), A2 = mul4(DBZ[j], dxb_txz), A3 = mul4(DBZ[j], dzf_tzz);
+                DivGuard dg;
+                dg.add(A0); dg.add(A1); dg.add(A2); dg.add(A3);
+                float4 t0 = fdivs(A0, g.dx, g.rdx), t1 = fdivs(A1, g.dz, g.rdz), t2 = fdivs(A2, g.dx, g.rdx), t3 = fdivs(A3, g.dz, g.rdz);
+                if (PML) {
+                    const float4 B0 = add4(mul4(PXN[j], q0), t0), B1 = add4(mul4(PZN[j], q1), t1);
+                    const float4 B2 = add4(mul4(PXN[j], q2), t2), B3 = add4(mul4(PZN[j], q3), t3);
+                    dg.add(B0); dg.add(B1); dg.add(B2); dg.add(B3);
+                    n0 = fdiv4(B0, PXD[j], RPXD[j]); n1 = fdiv4(B1, PZD[j], RPZD[j]); n2 = fdiv4(B2, PXD[j], RPXD[j]); n3 = fdiv4(B3, PZD[j], RPZD[j]);
+                } else {
+                    n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
+                }
+                if (!dg.ok()) {          // rare: a numerator in the underflow range -> the IEEE sequence
+                    t0 = ieee_divs(A0, g.dx); t1 = ieee_divs(A1, g.dz); t2 = ieee_divs(A2, g.dx); t3 = ieee_divs(A3, g.dz);
+                    if (PML) {
+                        n0 = ieee_div4(add4(mul4(PXN[j], q0), t0), PXD[j]); n1 = ieee_div4(add4(mul4(PZN[j], q1), t1), PZD[j]);
+                        n2 = ieee_div4(add4(mul4(PXN[j], q2), t2), PXD[j]); n3 = ieee_div4(add4(mul4(PZN[j], q3), t3), PZD[j]);
+                    } else {
+                        n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
+                    }
+                }
             }
             q0 = sel4(m, n0, q0); q1 = sel4(m, n1, q1); q2 = sel4(m, n2, q2); q3 = sel4(m, n3, q3);
             nvx[j] = add4(q0, q1); nvz[j] = add4(q2, q3);
@@ -577,7 +599,7 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
         }
         if (has_rcv) {                 // receivers of this tile (:405-409): new sums parked in the vxx / vzx rects
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { const int co = (R.r0 + j) * TX + R.c0; st4(cv + co, nvx[j]); st4(cv + 2 * CF + co, nvz[j]); }
+            for (int j = 0; j < RPT; ++j) { const int co = (R.r0 + j) * TX + R.c0; st4(cv + co, nvx[j]); st4(cv + 2 * CF + co, nvz[j]); }
             __syncthreads();
             for (int i = rcv_lo + tid; i < rcv_hi; i += NTH) {
                 const int r = a.rb.id[i], zx = a.rb.zx[i];
@@ -650,15 +672,25 @@ __device__ __forceinline__ void k1_cell(const EGeom& g, unsigned m, const float4
                                         float4& N0, float4& N1, float4& N2, float4& N3)
 {
     const float4 q1 = add4(L0, lvx), q2 = add4(L1, lvx), q3 = add4(L2, lvz), q4 = add4(L3, lvz);
+    const float4 A1 = muls(q1, g.dt), A2 = muls(q2, g.dt), A3 = muls(q3, g.dt), A4 = muls(q4, g.dt);
+    DivGuard dg;
+    dg.add(A1); dg.add(A2); dg.add(A3); dg.add(A4);
+    w1 = fdivs(A1, g.dx, g.rdx); w2 = fdivs(A2, g.dz, g.rdz); w3 = fdivs(A3, g.dx, g.rdx); w4 = fdivs(A4, g.dz, g.rdz);
     if (PML) {
-        w1 = fdiv4(fdivs(muls(q1, g.dt), g.dx, g.rdx), pxd, rpxd); w2 = fdiv4(fdivs(muls(q2, g.dt), g.dz, g.rdz), pzd, rpzd);
-        w3 = fdiv4(fdivs(muls(q3, g.dt), g.dx, g.rdx), pxd, rpxd); w4 = fdiv4(fdivs(muls(q4, g.dt), g.dz, g.rdz), pzd, rpzd);
-        N0 = fdiv4(mul4(pxn, q1), pxd, rpxd); N1 = fdiv4(mul4(pzn, q2), pzd, rpzd);
-        N2 = fdiv4(mul4(pxn, q3), pxd, rpxd); N3 = fdiv4(mul4(pzn, q4), pzd, rpzd);
+        const float4 B1 = mul4(pxn, q1), B2 = mul4(pzn, q2), B3 = mul4(pxn, q3), B4 = mul4(pzn, q4);
+        dg.add(w1); dg.add(w2); dg.add(w3); dg.add(w4); dg.add(B1); dg.add(B2); dg.add(B3); dg.add(B4);
+        w1 = fdiv4(w1, pxd, rpxd); w2 = fdiv4(w2, pzd, rpzd); w3 = fdiv4(w3, pxd, rpxd); w4 = fdiv4(w4, pzd, rpzd);
+        N0 = fdiv4(B1, pxd, rpxd); N1 = fdiv4(B2, pzd, rpzd); N2 = fdiv4(B3, pxd, rpxd); N3 = fdiv4(B4, pzd, rpzd);
     } else {
-        w1 = fdivs(muls(q1, g.dt), g.dx, g.rdx); w2 = fdivs(muls(q2, g.dt), g.dz, g.rdz);
-        w3 = fdivs(muls(q3, g.dt), g.dx, g.rdx); w4 = fdivs(muls(q4, g.dt), g.dz, g.rdz);
         N0 = q1; N1 = q2; N2 = q3; N3 = q4;
+    }
+    if (!dg.ok()) {              // rare: a numerator in the underflow range -> the IEEE sequence
+        w1 = ieee_divs(A1, g.dx); w2 = ieee_divs(A2, g.dz); w3 = ieee_divs(A3, g.dx); w4 = ieee_divs(A4, g.dz);
+        if (PML) {
+            w1 = ieee_div4(w1, pxd); w2 = ieee_div4(w2, pzd); w3 = ieee_div4(w3, pxd); w4 = ieee_div4(w4, pzd);
+            N0 = ieee_div4(mul4(pxn, q1), pxd); N1 = ieee_div4(mul4(pzn, q2), pzd);
+            N2 = ieee_div4(mul4(pxn, q3), pxd); N3 = ieee_div4(mul4(pzn, q4), pzd);
+        }
     }
     w1 = sel4(m, w1, zero4()); w2 = sel4(m, w2, zero4()); w3 = sel4(m, w3, zero4()); w4 = sel4(m, w4, zero4());
     m1 = mul4(w1, bx); m2 = mul4(w2, bx); m3 = mul4(w3, bz); m4 = mul4(w4, bz);
@@ -678,9 +710,9 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
     const unsigned cm = col_mask<NN>(gx, g.nxp);
     const bool col_ok = gx < g.ld;
     const size_t fp = (size_t)g.ns * g.plane;
-    float4 BX[2], BZ[2], PXN[2], PXD[2], PZN[2], PZD[2], RPXD[2], RPZD[2], GBX[2], GBZ[2];
+    float4 BX[RPT], BZ[RPT], PXN[RPT], PXD[RPT], PZN[RPT], PZD[RPT], RPXD[RPT], RPZD[RPT], GBX[RPT], GBZ[RPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPT; ++j) {
         const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
         BX[j] = ldk4(a.cp.bx + o, pol); BZ[j] = ldk4(a.cp.bz + o, pol);
         if (PML) {
@@ -708,9 +740,9 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         float* L = (float*)(smem + k * G::K1_STAGE);       // rects 0..3: velocity-split cotangents (become m1..m4), 4: lvx, 5: lvz
         float* lvx = L + 4 * (G::HB / 4); float* lvz = L + 5 * (G::HB / 4);
         // history of this step (own cells): e1 = D+x txx, e2 = D-z txz, e3 = D-x txz, e4 = D+z tzz
-        float4 E[4][2];
+        float4 E[4][RPT];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const int gz = gz0 + j;
             const float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + (size_t)gz * g.ld + gx;
 #pragma unroll
@@ -757,7 +789,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         }
         // ---- pass A: own-cell transpose; m1..m4 replace the split cotangents in the staged rects ------
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const int r = R.r0 + j, gz = gz0 + j;
             const int hb = (r + NN) * RXH + R.c0 + HX;
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
@@ -798,7 +830,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         {
             const float* M1 = L; const float* M2 = L + G::HB / 4; const float* M3 = L + 2 * (G::HB / 4); const float* M4 = L + 3 * (G::HB / 4);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < RPT; ++j) {
                 const int r = R.r0 + j, gz = gz0 + j;
                 const int hb = (r + NN) * RXH + R.c0 + HX;
                 float s1[12], s3[12];
@@ -835,7 +867,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPT; ++j) {
         const int gz = gz0 + j;
         if (col_ok && gz < g.nzp) {
             float* gp = a.gpart + (size_t)chunk * 6 * g.plane + (size_t)gz * g.ld + gx;
@@ -930,9 +962,9 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
     const bool col_ok = gx < g.ld;
     const size_t fp = (size_t)g.ns * g.plane;
     if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
-    float4 C11[2], C13[2], C33[2], C55[2], PXN[2], PXI[2], PZN[2], PZI[2], G11[2], G13[2], G33[2], G55[2];
+    float4 C11[RPT], C13[RPT], C33[RPT], C55[RPT], PXN[RPT], PXI[RPT], PZN[RPT], PZI[RPT], G11[RPT], G13[RPT], G33[RPT], G55[RPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPT; ++j) {
         const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
         C11[j] = ldk4(a.cp.c11 + o, pol); C13[j] = ldk4(a.cp.c13 + o, pol);
         C33[j] = ldk4(a.cp.c33 + o, pol); C55[j] = ldk4(a.cp.c55 + o, pol);
@@ -958,9 +990,9 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         float* mzz_r = MS + HQ; float* mxz_r = MS + 2 * HQ;
         float* LSr = MS + 3 * HQ;                           // rects LS0, LS1, LS4, LS5 become nA, nB, nC, nD
         // history of this step (own cells): D-x vx, D-z vz, D+x vz, D+z vx
-        float4 D[4][2];
+        float4 D[4][RPT];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const int gz = gz0 + j;
             const float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + (size_t)gz * g.ld + gx;
 #pragma unroll
@@ -984,7 +1016,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         }
         // ---- pass A: own-cell transpose; nA..nD replace four of the split cotangents in the staged rects ----
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < RPT; ++j) {
             const int r = R.r0 + j, gz = gz0 + j;
             const int hb = (r + NN) * RXH + R.c0 + HX;
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
@@ -1039,7 +1071,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         {
             const float* NA = LSr; const float* NB = LSr + HQ; const float* NC = LSr + 4 * HQ; const float* ND = LSr + 5 * HQ;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < RPT; ++j) {
                 const int r = R.r0 + j, gz = gz0 + j;
                 const int hb = (r + NN) * RXH + R.c0 + HX;
                 float sa[12], sc[12];
@@ -1064,7 +1096,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPT; ++j) {
         const int gz = gz0 + j;
         if (col_ok && gz < g.nzp) {
             float* gp = a.gpart + (size_t)chunk * 6 * g.plane + (size_t)gz * g.ld + gx;
