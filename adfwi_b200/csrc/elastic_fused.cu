@@ -39,7 +39,7 @@ constexpr int TX = 64, TZ = 16;             // tile interior
 constexpr int HX = 4;                       // x halo of the staged rectangles (one float4 group)
 constexpr int RXH = TX + 2 * HX;            // 72 floats per halo row
 constexpr int NG = TX / 4;                  // float4 groups per tile row
-constexpr int RPT = 2;                      // tile rows per thread
+constexpr int RPT = 1;                      // tile rows per thread
 constexpr int NTH = NG * (TZ / RPT);        // threads per CTA: one float4 group x RPT rows each
 constexpr int CMAX = 32;                    // max shots per chunk
 constexpr int CPX = 4, CPZ = 4;             // apron of the coefficient pack
@@ -78,7 +78,7 @@ struct EGeom {
 };
 struct ECoef { const float *c11, *c13, *c33, *c55, *bx, *bz, *bcx, *bcz; };   // pack planes, pre-offset to cell (0,0)
 struct RcvB { const int* start; const int* id; const int* zx; const unsigned char* nbr; };
-struct Walk { int s_begin, s_end, chunk, nchunks; };
+struct Walk { int s_begin, s_end, chunk, nchunks; int* counter; };
 
 struct SArgs { ECoef cp; const unsigned char* tflags; float* planes; const float* mt; const float* src_v;
                const int64_t *sx, *sz; float* hist; int hist_len, tl, it; Walk w; };
@@ -240,9 +240,12 @@ template <int NN> __device__ __forceinline__ float4 zgath(const float4* w, const
     return v;
 }
 
-// (tile, shot) sequence of one persistent CTA: items blockIdx.x, +gridDim.x, ...
+// (tile, shot) sequence of one persistent CTA.  Items = (tile, chunk of the launch's shots); the first item of a CTA
+// is blockIdx.x, the following ones are drawn from the launch's atomic counter (dynamic balancing: PML tiles and
+// ragged chunks cost differently).  Only thread 0 -- the TMA producer, running NSTAGE shots ahead of the compute --
+// keeps a cursor; the ids it draws are handed to the consumers through a 4-entry ring in shared memory.
 struct Cursor {
-    int item, s, s_hi, X0, Z0; bool valid;
+    int item, s, s_hi, X0, Z0; bool valid; unsigned wr;
     __device__ __forceinline__ void set(int it, const EGeom& g, const Walk& w)
     {
         item = it; valid = it < g.ntx * g.ntz * w.nchunks;
@@ -253,9 +256,13 @@ struct Cursor {
             s = w.s_begin + ch * w.chunk; s_hi = min(s + w.chunk, w.s_end);
         }
     }
-    __device__ __forceinline__ void next(const EGeom& g, const Walk& w)
+    __device__ __forceinline__ void next(const EGeom& g, const Walk& w, int* ring)
     {
-        if (valid && ++s >= s_hi) set(item + gridDim.x, g, w);
+        if (valid && ++s >= s_hi) {
+            const int it = (int)gridDim.x + atomicAdd(w.counter, 1);
+            ring[wr++ & 3u] = it;
+            set(it, g, w);
+        }
     }
 };
 
@@ -302,7 +309,7 @@ template <int NN> __device__ __forceinline__ void s_issue(const Cursor& c, unsig
 
 template <int NN, bool PML, bool FS, bool SAVE>
 __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap* tc, const EGeom& g, const SArgs& a,
-                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
                                        int* s_sz, int* s_sx, float* s_sxx, float* s_szz, float* s_sxz,
                                        const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
 {
@@ -337,7 +344,7 @@ __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap*
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (pc.valid) { if (tid == 0) s_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+            if (tid == 0 && pc.valid) { s_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w, ring); }
     }
     __syncthreads();
 
@@ -431,7 +438,7 @@ __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap*
         }
         if (FS && tzi == 0) fence_proxy_async();
         __syncthreads();
-        if (pc.valid) { if (tid == 0) s_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+        if (tid == 0 && pc.valid) { s_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 }
@@ -455,16 +462,19 @@ elf_s(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     uint32_t par = 0;
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    int* ring = (int*)(bar + 4);
     Cursor pc;
+    pc.wr = 0;
     pc.set(blockIdx.x, g, a.w);
     griddep_launch_dependents();
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    unsigned rd = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < nitems; item = ring[rd++ & 3u], first = false) {
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) s_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
-        else                s_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        if (a.tflags[tile]) s_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        else                s_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -487,7 +497,7 @@ template <int NN> __device__ __forceinline__ void v_issue(const Cursor& c, unsig
 
 template <int NN, bool PML, bool FS, bool SAVE>
 __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap* tc, const EGeom& g, const VArgs& a,
-                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
                                        const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
 {
     using G = Geo<NN>;
@@ -515,7 +525,7 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (pc.valid) { if (tid == 0) v_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+            if (tid == 0 && pc.valid) { v_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w, ring); }
     }
 
     for (int s = s_lo; s < s_hi; ++s) {
@@ -612,7 +622,7 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
         }
         if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
         __syncthreads();
-        if (pc.valid) { if (tid == 0) v_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w); }
+        if (tid == 0 && pc.valid) { v_issue<NN>(pc, smem, bar, k, th, tc, g.ns); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 }
@@ -631,16 +641,19 @@ elf_v(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     uint32_t par = 0;
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    int* ring = (int*)(bar + 4);
     Cursor pc;
+    pc.wr = 0;
     pc.set(blockIdx.x, g, a.w);
     griddep_launch_dependents();
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    unsigned rd = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < nitems; item = ring[rd++ & 3u], first = false) {
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) v_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, R, tid, tile, s_lo, s_hi, first);
-        else                v_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, R, tid, tile, s_lo, s_hi, first);
+        if (a.tflags[tile]) v_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
+        else                v_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -699,7 +712,7 @@ __device__ __forceinline__ void k1_cell(const EGeom& g, unsigned m, const float4
 
 template <int NN, bool PML, bool FS>
 __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, const K1Args& a,
-                                        unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                        unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
                                         const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
 {
     using G = Geo<NN>;
@@ -732,7 +745,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (pc.valid) { if (tid == 0) k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+            if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
     }
 
     for (int s = s_lo; s < s_hi; ++s) {
@@ -863,7 +876,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         }
         fence_proxy_async();
         __syncthreads();
-        if (pc.valid) { if (tid == 0) k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+        if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -890,16 +903,19 @@ elf_k1(const __grid_constant__ CUtensorMap th, const EGeom g, const K1Args a)
     uint32_t par = 0;
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    int* ring = (int*)(bar + 4);
     Cursor pc;
+    pc.wr = 0;
     pc.set(blockIdx.x, g, a.w);
     griddep_launch_dependents();
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    unsigned rd = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < nitems; item = ring[rd++ & 3u], first = false) {
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) k1_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, R, tid, tile, chunk, s_lo, s_hi, first);
-        else                k1_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, R, tid, tile, chunk, s_lo, s_hi, first);
+        if (a.tflags[tile]) k1_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                k1_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -949,7 +965,7 @@ __device__ __forceinline__ void k2_cell(const EGeom& g, unsigned m, const float4
 
 template <int NN, bool PML, bool FS>
 __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, const K2Args& a,
-                                        unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc,
+                                        unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
                                         int* s_sz, int* s_sx, const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
 {
     using G = Geo<NN>;
@@ -980,7 +996,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (pc.valid) { if (tid == 0) k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+            if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
     }
     __syncthreads();
 
@@ -1092,7 +1108,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         }
         fence_proxy_async();
         __syncthreads();
-        if (pc.valid) { if (tid == 0) k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w); }
+        if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -1121,16 +1137,19 @@ elf_k2(const __grid_constant__ CUtensorMap th, const EGeom g, const K2Args a)
     uint32_t par = 0;
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    int* ring = (int*)(bar + 4);
     Cursor pc;
+    pc.wr = 0;
     pc.set(blockIdx.x, g, a.w);
     griddep_launch_dependents();
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    unsigned rd = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < nitems; item = ring[rd++ & 3u], first = false) {
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) k2_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
-        else                k2_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        if (a.tflags[tile]) k2_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                k2_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -1267,6 +1286,7 @@ struct EFPlan {
     float* pack; unsigned char* tflags;
     float* planes; int nfields;
     float *hist, *ckpt, *gpart, *ill;
+    int* counters; int ncounters;       // one work counter per launch of a call
     int *rcv_cnt, *rcv_start, *rcv_cursor, *rcv_id, *rcv_zx; unsigned char* rcv_nbr;
     size_t bytes;
 };
@@ -1310,6 +1330,8 @@ int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
     P->rcv_cnt = cv.take<int>(ntiles + 1); P->rcv_start = cv.take<int>(ntiles + 1); P->rcv_cursor = cv.take<int>(ntiles + 1);
     P->rcv_id = cv.take<int>(d->nr > 0 ? d->nr : 1); P->rcv_zx = cv.take<int>(d->nr > 0 ? d->nr : 1);
     P->rcv_nbr = cv.take<unsigned char>(ntiles);
+    P->ncounters = 4 * d->nt * cdiv(d->ns, G) + 64;
+    P->counters = cv.take<int>(P->ncounters);
     P->hist = P->ckpt = P->gpart = nullptr;
     if (P->save) {
         P->gpart = cv.take<float>((size_t)P->nchunks * 6 * g.plane);
@@ -1409,7 +1431,7 @@ template <int NN> int elf_init_kernels()
 
 inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid)
 {
-    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = P.chunk; w.nchunks = cdiv(se - sb, P.chunk);
+    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = P.chunk; w.nchunks = cdiv(se - sb, P.chunk); w.counter = nullptr;
     const int nitems = P.g.ntx * P.g.ntz * w.nchunks;
     const int cap = CTAS_PER_SM * elf_num_sms();
     *grid = nitems < cap ? nitems : cap;
@@ -1421,8 +1443,9 @@ struct EArgs { const float *mt, *src_v; const int64_t *sx, *sz; };
 // one forward step of shots [sb,se): elf_s then elf_v
 template <int NN>
 int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, int se, int it, bool save, int tl,
-                     const EArgs& ea, float* const* rcv)
+                     const EArgs& ea, float* const* rcv, int* seq)
 {
+    if (*seq + 2 > P.ncounters) return ADFWI_E_DIMS;
     const EGeom& g = P.g;
     int grid;
     const Walk w = elf_walk(P, sb, se, &grid);
@@ -1430,7 +1453,7 @@ int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, i
     {
         SArgs a;
         a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.mt = ea.mt; a.src_v = ea.src_v; a.sx = ea.sx; a.sz = ea.sz;
-        a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it; a.w = w;
+        a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it; a.w = w; a.w.counter = P.counters + (*seq)++;
         TimedLaunch tl_(KC_EL_FWD_STRESS, st);
         if (P.FS) { if (save) ADFWI_CUDA(elf_launch(elf_s<NN, true, true>, grid, s_smem<NN>(), st, pdl, M.halo, M.core, g, a));
                     else      ADFWI_CUDA(elf_launch(elf_s<NN, true, false>, grid, s_smem<NN>(), st, pdl, M.halo, M.core, g, a)); }
@@ -1443,7 +1466,7 @@ int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, i
         a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it;
         a.nr = rcv ? P.nr : 0; a.rb = elf_bucket_ptrs(P);
         for (int k = 0; k < 5; ++k) a.rcv[k] = rcv ? rcv[k] : nullptr;
-        a.w = w;
+        a.w = w; a.w.counter = P.counters + (*seq)++;
         TimedLaunch tl_(KC_EL_FWD_VEL, st);
         if (P.FS) { if (save) ADFWI_CUDA(elf_launch(elf_v<NN, true, true>, grid, v_smem<NN>(), st, pdl, M.halo, M.core, g, a));
                     else      ADFWI_CUDA(elf_launch(elf_v<NN, true, false>, grid, v_smem<NN>(), st, pdl, M.halo, M.core, g, a)); }
@@ -1483,6 +1506,8 @@ int elf_forward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs&
     const int csz = cdiv(nt, P.n_segments);
     const int nphys = P.nz * P.nx;
     if (illum) ADFWI_CUDA(cudaMemsetAsync(P.ill, 0, sizeof(float) * 5 * nphys, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(int) * P.ncounters, st));
+    int seq = 0;
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
         int rc = elf_zero_fields(P, st, 0, P_FWD_COUNT, sb, se);
@@ -1494,7 +1519,7 @@ int elf_forward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs&
                 if (rc) return rc;
             }
             const bool save = P.save && seg == P.nseg - 1;
-            rc = elf_forward_step<NN>(P, M, st, sb, se, it, save, tl, ea, P.nr > 0 ? rcv : nullptr);
+            rc = elf_forward_step<NN>(P, M, st, sb, se, it, save, tl, ea, P.nr > 0 ? rcv : nullptr, &seq);
             if (rc) return rc;
             if (illum && ((it + 1) % csz == 0 || it == nt - 1)) {
                 elf_illum_acc<<<dim3(cdiv(P.nx, 128), P.nz), 128, 0, st>>>(g, NN, P.nz, P.nx, P.nabc, P.zoff, sb, se, P.planes, P.ill);
@@ -1516,6 +1541,8 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
     const int nt = g.nt;
     const bool pdl = elf_use_pdl();
     ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks * 6 * g.plane, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(int) * P.ncounters, st));
+    int seq = 0;
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
         int rc = elf_zero_fields(P, st, P_LV, P_COUNT, sb, se);
@@ -1530,7 +1557,7 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                 else          rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, false);
                 if (rc) return rc;
                 for (int it = t0; it < t1; ++it) {
-                    rc = elf_forward_step<NN>(P, M, st, sb, se, it, true, it - t0, ea, nullptr);
+                    rc = elf_forward_step<NN>(P, M, st, sb, se, it, true, it - t0, ea, nullptr, &seq);
                     if (rc) return rc;
                 }
             }
@@ -1540,7 +1567,8 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                     a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
                     a.nr = P.nr; a.rb = elf_bucket_ptrs(P);
                     for (int k = 0; k < 5; ++k) a.g[k] = g_rcv[k];
-                    a.gpart = P.gpart; a.w = w;
+                    if (seq + 2 > P.ncounters) return ADFWI_E_DIMS;
+                    a.gpart = P.gpart; a.w = w; a.w.counter = P.counters + seq++;
                     TimedLaunch tl_(KC_EL_ADJ_VEL, st);
                     if (P.FS) ADFWI_CUDA(elf_launch(elf_k1<NN, true>, grid, k1_smem<NN>(), st, pdl, M.halo, g, a));
                     else      ADFWI_CUDA(elf_launch(elf_k1<NN, false>, grid, k1_smem<NN>(), st, pdl, M.halo, g, a));
@@ -1549,7 +1577,7 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                 {
                     K2Args a;
                     a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
-                    a.mt = ea.mt; a.sx = ea.sx; a.sz = ea.sz; a.g_src = g_src; a.gpart = P.gpart; a.w = w;
+                    a.mt = ea.mt; a.sx = ea.sx; a.sz = ea.sz; a.g_src = g_src; a.gpart = P.gpart; a.w = w; a.w.counter = P.counters + seq++;
                     TimedLaunch tl_(KC_EL_ADJ_STRESS, st);
                     if (P.FS) ADFWI_CUDA(elf_launch(elf_k2<NN, true>, grid, k2_smem<NN>(), st, pdl, M.halo, g, a));
                     else      ADFWI_CUDA(elf_launch(elf_k2<NN, false>, grid, k2_smem<NN>(), st, pdl, M.halo, g, a));
