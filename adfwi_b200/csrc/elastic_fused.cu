@@ -115,6 +115,12 @@ __device__ __forceinline__ void red4(float* p, const float4& v)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// TMA prefetch of a box into L2 (no shared-memory destination): used for the history planes, which the adjoint
+// kernels then read with plain 128-bit loads -- an L2 hit instead of a DRAM round trip on the critical path
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -662,8 +668,10 @@ elf_v(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
 // elf_k1 : adjoint of the velocity update
 // ==========================================================================================
 template <int NN> __device__ __forceinline__ void k1_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
-                                                           const CUtensorMap* th, int ns, int lcur)
+                                                           const CUtensorMap* th, int ns, int lcur, const CUtensorMap* thh, int hist_len, int tl)
 {
+#pragma unroll
+    for (int e = 4; e < 8; ++e) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
     using G = Geo<NN>;
     unsigned char* st = smem + k * G::K1_STAGE;
     fence_proxy_async();
@@ -711,7 +719,7 @@ __device__ __forceinline__ void k1_cell(const EGeom& g, unsigned m, const float4
 }
 
 template <int NN, bool PML, bool FS>
-__device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, const K1Args& a,
+__device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap* thh, const EGeom& g, const K1Args& a,
                                         unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
                                         const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
 {
@@ -745,7 +753,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
+            if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
     }
 
     for (int s = s_lo; s < s_hi; ++s) {
@@ -876,7 +884,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
+        if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -891,7 +899,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const EGeom& g, c
 
 template <int NN, bool FS>
 __global__ void __launch_bounds__(NTH, 2)
-elf_k1(const __grid_constant__ CUtensorMap th, const EGeom g, const K1Args a)
+elf_k1(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap thh, const EGeom g, const K1Args a)
 {
     using G = Geo<NN>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -914,8 +922,8 @@ elf_k1(const __grid_constant__ CUtensorMap th, const EGeom g, const K1Args a)
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) k1_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
-        else                k1_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
+        if (a.tflags[tile]) k1_tile<NN, true, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                k1_tile<NN, false, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -924,8 +932,10 @@ elf_k1(const __grid_constant__ CUtensorMap th, const EGeom g, const K1Args a)
 // elf_k2 : adjoint of the stress update (Appendix A.2, steps 5T..1T)
 // ==========================================================================================
 template <int NN> __device__ __forceinline__ void k2_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
-                                                           const CUtensorMap* th, int ns, int lcur)
+                                                           const CUtensorMap* th, int ns, int lcur, const CUtensorMap* thh, int hist_len, int tl)
 {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
     using G = Geo<NN>;
     unsigned char* st = smem + k * G::K2_STAGE;
     fence_proxy_async();
@@ -964,7 +974,7 @@ __device__ __forceinline__ void k2_cell(const EGeom& g, unsigned m, const float4
 }
 
 template <int NN, bool PML, bool FS>
-__device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, const K2Args& a,
+__device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap* thh, const EGeom& g, const K2Args& a,
                                         unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
                                         int* s_sz, int* s_sx, const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
 {
@@ -996,7 +1006,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
+            if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
     }
     __syncthreads();
 
@@ -1108,7 +1118,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur); pc.next(g, a.w, ring); }
+        if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -1123,7 +1133,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const EGeom& g, c
 
 template <int NN, bool FS>
 __global__ void __launch_bounds__(NTH, 2)
-elf_k2(const __grid_constant__ CUtensorMap th, const EGeom g, const K2Args a)
+elf_k2(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap thh, const EGeom g, const K2Args a)
 {
     using G = Geo<NN>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1148,8 +1158,8 @@ elf_k2(const __grid_constant__ CUtensorMap th, const EGeom g, const K2Args a)
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) k2_tile<NN, true, FS>(&th, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
-        else                k2_tile<NN, false, FS>(&th, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        if (a.tflags[tile]) k2_tile<NN, true, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                k2_tile<NN, false, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -1379,14 +1389,16 @@ int elf_setup(const EFPlan& P, cudaStream_t st, const float* const* coef, const 
     return ADFWI_OK;
 }
 
-struct EMaps { CUtensorMap halo, core; };
+struct EMaps { CUtensorMap halo, core, hist; };
 
 int elf_make_maps(const EFPlan& P, EMaps* M)
 {
     const EGeom& g = P.g;
     int rc = make_tmap_f32(&M->halo, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, RXH, TZ + 2 * P.NN);
     if (rc) return rc;
-    return make_tmap_f32(&M->core, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, TX, TZ);
+    rc = make_tmap_f32(&M->core, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, TX, TZ);
+    if (rc || !P.save) return rc;
+    return make_tmap_f32(&M->hist, P.hist, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.ns * P.K * NHIST, TX, TZ);
 }
 
 template <typename Kern, typename... Args>
@@ -1570,8 +1582,8 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                     if (seq + 2 > P.ncounters) return ADFWI_E_DIMS;
                     a.gpart = P.gpart; a.w = w; a.w.counter = P.counters + seq++;
                     TimedLaunch tl_(KC_EL_ADJ_VEL, st);
-                    if (P.FS) ADFWI_CUDA(elf_launch(elf_k1<NN, true>, grid, k1_smem<NN>(), st, pdl, M.halo, g, a));
-                    else      ADFWI_CUDA(elf_launch(elf_k1<NN, false>, grid, k1_smem<NN>(), st, pdl, M.halo, g, a));
+                    if (P.FS) ADFWI_CUDA(elf_launch(elf_k1<NN, true>, grid, k1_smem<NN>(), st, pdl, M.halo, M.hist, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_k1<NN, false>, grid, k1_smem<NN>(), st, pdl, M.halo, M.hist, g, a));
                 }
                 ADFWI_LAUNCH_CHECK();
                 {
@@ -1579,8 +1591,8 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                     a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
                     a.mt = ea.mt; a.sx = ea.sx; a.sz = ea.sz; a.g_src = g_src; a.gpart = P.gpart; a.w = w; a.w.counter = P.counters + seq++;
                     TimedLaunch tl_(KC_EL_ADJ_STRESS, st);
-                    if (P.FS) ADFWI_CUDA(elf_launch(elf_k2<NN, true>, grid, k2_smem<NN>(), st, pdl, M.halo, g, a));
-                    else      ADFWI_CUDA(elf_launch(elf_k2<NN, false>, grid, k2_smem<NN>(), st, pdl, M.halo, g, a));
+                    if (P.FS) ADFWI_CUDA(elf_launch(elf_k2<NN, true>, grid, k2_smem<NN>(), st, pdl, M.halo, M.hist, g, a));
+                    else      ADFWI_CUDA(elf_launch(elf_k2<NN, false>, grid, k2_smem<NN>(), st, pdl, M.halo, M.hist, g, a));
                 }
                 ADFWI_LAUNCH_CHECK();
                 lcur ^= 1;
