@@ -50,3 +50,24 @@ def acoustic_gradient(propagator, obs_p: torch.Tensor, shots: Optional[Sequence[
         fw = rec["forward_wavefield_p"]
         illum = fw if illum is None else illum + fw
     return total, illum
+
+
+def elastic_gradient(propagator, obs: dict, shots: Optional[Sequence[int]] = None, batch_size: Optional[int] = None,
+                     components: Sequence[str] = ("vx", "vz"), fd_order: int = 4, checkpoint_segments: int = 1,
+                     obs_loader: Optional[Callable] = None):
+    """Elastic counterpart of :func:`acoustic_gradient` (the shot-batch loop of ElasticFWI.forward,
+    ADFWI/fwi/elastic_fwi.py:200-277): L2 waveform misfit summed over ``components`` of the records.
+    ``obs[c]`` is indexed by position in ``shots``; ``obs_loader(positions) -> {c: tensor}`` streams a batch instead.
+    Returns (loss tensor on device, summed forward_wavefield_vz illumination)."""
+    shots = np.arange(propagator.src_n) if shots is None else np.asarray(shots)
+    total = None
+    illum = None
+    for pos in shot_batches(len(shots), batch_size):
+        rec = propagator.forward(shot_index=shots[pos], fd_order=fd_order, checkpoint_segments=checkpoint_segments)
+        ob = obs_loader(pos) if obs_loader is not None else {c: obs[c][pos] for c in components}
+        loss = sum(l2_waveform_misfit(ob[c], rec[c], propagator.dt) for c in components)
+        loss.backward()
+        total = loss.detach() if total is None else total + loss.detach()
+        fw = rec["forward_wavefield_vz"]
+        illum = fw if illum is None else illum + fw
+    return total, illum

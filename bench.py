@@ -35,6 +35,10 @@ WORKLOADS = {
                desc="iso-acoustic Marmousi2 example 88x200 (148x260 padded), nt=1600"),
     "C2": dict(nz=350, nx=1700, dx=10.0, dt=1e-3, nt=4000, f0=10.0, nabc=50, shots8=240, nr=1700, batch=10,
                desc="iso-acoustic Marmousi2 full-res 350x1700 (450x1800 padded), nt=4000, 240 shots / 8 GPUs"),
+    "C3": dict(kind="elastic", nz=350, nx=1700, dx=10.0, dt=1e-3, nt=4000, f0=10.0, nabc=50, shots8=240, nr=1700, batch=15, z_sr=10,
+               desc="iso-elastic Marmousi2 350x1700 (402x1800 padded), split-PML O(2,4), free surface, nt=4000, vp/vs/rho gradients, 240 shots / 8 GPUs"),
+    "C4": dict(kind="elastic", nz=320, nx=720, dx=2.5, dt=2.5e-4, nt=4000, f0=30.0, nabc=50, shots8=120, nr=720, batch=5, z_sr=10, vti=True,
+               desc="VTI-elastic 320x720 (372x820 padded), split-PML O(2,4), free surface, nt=4000, eps/delta gradients, 120 shots / 8 GPUs"),
     "C5": dict(nz=2048, nx=8192, dx=5.0, dt=5e-4, nt=1000, f0=15.0, nabc=50, shots8=8 * 2, nr=8192, batch=2,
                desc="synthetic acoustic 2048x8192 (2148x8292 padded), 1000-step slice of nt=8000, 2 shots/GPU"),
 }
@@ -42,6 +46,10 @@ WORKLOADS = {
 B_FWD_SAVE = 36.0     # forward sweep in recording mode: p,u,w r+w 24 + alpha1,alpha2 8 + S write 4
 B_ADJ = 44.0          # adjoint sweep (vp only): 3 adjoint fields r+w 24 + alpha1,alpha2 8 + S read 4 + g_alpha1 RMW 8
 B_GRAD_STEP = 80.0    # forward(recording) + adjoint per cell-step = 40 B per cell-update
+# elastic split-PML: forward 104 B (+20 B recording), adjoint 124 B (+ gradient RMW amortised over the shots)
+B_EL_FWD_SAVE = 124.0
+B_EL_ADJ = 124.0
+B_EL_GRAD_STEP = 248.0
 
 
 def measured_peak_gbs():
@@ -106,6 +114,8 @@ def cpu_gradient_sample(wl, ns, nt):
     from oracle import oracle as O
     from adfwi_b200 import synthetic as syn
     from adfwi_b200.propagator.boundary_condition import bc_pml
+    if wl.get("kind") == "elastic":
+        return cpu_elastic_sample(wl, ns, nt)
     nz, nx, nabc = wl["nz"], wl["nx"], wl["nabc"]
     vp = syn.smooth2d(syn.marmousi_like_vp(nz, nx), 6)
     rho = syn.gardner_rho(vp)
@@ -121,6 +131,47 @@ def cpu_gradient_sample(wl, ns, nt):
                    need_g_alpha2=False)
     sec = time.perf_counter() - t0
     cells = (nz + 2 * nabc) * (nx + 2 * nabc) * ns * nt
+    return 2.0 * cells / sec, sec
+
+
+def elastic_fields(wl):
+    """Synthetic iso / VTI elastic model of a workload: (true vp, initial vp, vs, rho, eps, delta) as numpy planes."""
+    from adfwi_b200 import synthetic as syn
+    nz, nx = wl["nz"], wl["nx"]
+    vp_true = syn.marmousi_like_vp(nz, nx)
+    vp = syn.smooth2d(vp_true, 6)
+    mk = lambda v: (v / np.sqrt(3.0)).astype(np.float32)
+    eps = np.full((nz, nx), 0.1 if wl.get("vti") else 0.0, np.float32)
+    delta = np.full((nz, nx), -0.1 if wl.get("vti") else 0.0, np.float32)
+    return vp_true, vp, mk, syn.gardner_rho, eps, delta
+
+
+def cpu_elastic_sample(wl, ns, nt):
+    """Elastic counterpart of cpu_gradient_sample: the oracle's split-PML forward + adjoint."""
+    from oracle import oracle as O
+    from adfwi_b200 import synthetic as syn
+    from adfwi_b200.propagator.boundary_condition import bc_pml_xz
+    nz, nx, nabc, dx = wl["nz"], wl["nx"], wl["nabc"], wl["dx"]
+    _, vp, mk_vs, mk_rho, eps, delta = elastic_fields(wl)
+    vs, rho = mk_vs(vp), mk_rho(vp)
+    C33 = vp * vp * rho; C44 = vs * vs * rho; C11 = C33 * (1 + 2 * eps)
+    C13 = np.sqrt(2 * C33 * (C33 - C44) * delta + (C33 - C44) ** 2) - C44
+    b = 1.0 / rho
+    C55 = 0.2 * (C44[1:-1, 1:-1] + C44[2:, 1:-1] + C44[1:-1, 2:] + C44[2:, 1:-1] + C44[2:, 2:])
+    planes = dict(C11=C11, C13=C13, C33=C33, C55=C55, bx=0.5 * (b[:, :-1] + b[:, 1:]), bz=0.5 * (b[:-1] + b[1:]))
+    planes = {k: v.astype(np.float32) for k, v in planes.items()}
+    bcx, bcz = bc_pml_xz(nx, nz, dx, dx, pml=nabc, vmax=float(vp.max()), free_surface=True)
+    z = wl["z_sr"]
+    sx = np.round(np.linspace(2, nx - 3, ns)).astype(np.int64); sz = np.full(ns, z, np.int64)
+    rx = np.round(np.linspace(0, nx - 1, wl["nr"])).astype(np.int64); rz = np.full(wl["nr"], z, np.int64)
+    wav = np.broadcast_to(syn.integrated_ricker(nt, wl["dt"], wl["f0"] * 4).astype(np.float32), (ns, nt)).copy()
+    mt = np.broadcast_to(np.eye(3, dtype=np.float32), (ns, 3, 3)).copy()
+    O.lib().oracle_set_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    O.elastic_run(planes, "PML", 4, True, nz, nx, nabc, dx, dx, wl["dt"], sx, sz, wav, mt, rx, rz, bcx=bcx.astype(np.float32),
+                  bcz=bcz.astype(np.float32), g_rcv=lambda rec: (None, None, None, rec["vx"], rec["vz"]))
+    sec = time.perf_counter() - t0
+    cells = (nz + nabc + 2) * (nx + 2 * nabc) * ns * nt
     return 2.0 * cells / sec, sec
 
 
@@ -331,6 +382,174 @@ def run_b200(args, wl):
         dist.destroy_process_group()
 
 
+def run_b200_elastic(args, wl):
+    """C3 / C4: split-PML elastic FWI gradient (vx, vz misfit) through ElasticPropagator.forward() + backward()."""
+    import torch
+    import torch.distributed as dist
+    from adfwi_b200 import _lib, distributed as D, fwi, synthetic as syn
+    from adfwi_b200.propagator import ElasticPropagator
+
+    rank, local, world = D.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    _lib.load()
+
+    nz, nx, nabc, nt, dt, dx = wl["nz"], wl["nx"], wl["nabc"], wl["nt"], wl["dt"], wl["dx"]
+    if args.nt:
+        nt = args.nt
+    ns_local = args.shots or max(wl["shots8"] // 8, 1)
+    ns_total = ns_local * world
+    lo, hi = D.shard_shots(ns_total, rank, world)
+    batch = min(args.batch or wl["batch"], ns_local)
+    NN = 2
+    nzp, nxp = nz + nabc + NN, nx + 2 * nabc
+    comps = ("vx", "vz")
+    vp_true, vp_init, mk_vs, mk_rho, eps, delta = elastic_fields(wl)
+    grads = ("eps", "delta") if wl.get("vti") else ("vp", "vs", "rho")
+    survey = syn.surface_survey(nx, ns_total, wl["nr"], nt, dt, wl["f0"], src_z=wl["z_sr"], rcv_z=wl["z_sr"])
+    mk = lambda vp, req: syn.ElasticGridModel(vp, mk_vs(vp), mk_rho(vp), eps=eps, delta=delta, dx=dx, dz=dx, nabc=nabc,
+                                              free_surface=True, abc_type="PML", requires_grad=req, device=dev)
+    true_model, model = mk(vp_true, ()), mk(vp_init, grads)
+    prop_true = ElasticPropagator(true_model, survey, device=dev)
+    prop = ElasticPropagator(model, survey, device=dev)
+    prop.bcx, prop.bcz = prop_true.bcx, prop_true.bcz
+    shots = np.arange(lo, hi)
+    params = [getattr(model, k) for k in grads]
+
+    obs = {c: torch.empty((len(shots), nt, wl["nr"]), device=dev) for c in comps}
+    with torch.no_grad():
+        for pos in fwi.shot_batches(len(shots), batch):
+            rec = prop_true.forward(shot_index=shots[pos])
+            for c in comps:
+                obs[c][pos] = rec[c]
+            del rec
+    obs_host = {c: obs[c].cpu().pin_memory() for c in comps}
+    par_host = [p.detach().cpu().pin_memory() for p in params]
+    wav_host = prop.wavelet.detach().cpu().pin_memory()
+    grad_host = [torch.empty((nz, nx), dtype=torch.float32).pin_memory() for _ in params]
+    del prop_true, true_model
+    torch.cuda.empty_cache()
+
+    def step_resident():
+        for p in params:
+            p.grad = None
+        loss, illum = fwi.elastic_gradient(prop, obs, shots=shots, batch_size=batch, components=comps)
+        D.allreduce_gradients(params, extras=[illum, loss])
+        return loss
+
+    def step_e2e():
+        for p in params:
+            p.grad = None
+        with torch.no_grad():
+            for p, h in zip(params, par_host):
+                p.copy_(h, non_blocking=True)
+            prop.wavelet.copy_(wav_host, non_blocking=True)
+        loader = lambda pos: {c: obs_host[c][pos[0]:pos[-1] + 1].to(dev, non_blocking=True) for c in comps}
+        loss, illum = fwi.elastic_gradient(prop, None, shots=shots, batch_size=batch, components=comps, obs_loader=loader)
+        D.allreduce_gradients(params, extras=[illum, loss])
+        for p, h in zip(params, grad_host):
+            h.copy_(p.grad, non_blocking=True)
+        return float(loss.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start(); time.sleep(0.3)
+    n0 = _lib.launch_count()
+    _lib.timing_collect()
+    _lib.timing_enable(max(16 * args.steps, 16))
+    t_wall0 = time.time()
+    ms = timed(step_resident, args.steps)
+    t_wall1 = time.time()
+    _lib.timing_enable(0)
+    launches = _lib.launch_count() - n0
+    kt = _lib.timing_collect()
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    updates_per_step = 2.0 * nzp * nxp * nt * ns_total
+    value = updates_per_step * args.steps / (ms * 1e-3) / 1e9
+    e2e_value = updates_per_step * args.steps / (ms_e2e * 1e-3) / 1e9
+    lt = torch.tensor([float(launches)], device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    h2d = sum(h.numel() for h in par_host) * 4 + wav_host.numel() * 4 + sum(h.numel() for h in obs_host.values()) * 4
+    d2h = sum(h.numel() for h in grad_host) * 4 + 4
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        avg = {k: v[0] / v[1] for k, v in kt.items()}
+        roof = None
+        adj = avg.get("el_adj_vel", 0.0) + avg.get("el_adj_stress", 0.0)
+        fwd = avg.get("el_fwd_stress", 0.0) + avg.get("el_fwd_vel", 0.0)
+        cells = batch * nzp * nxp            # one launch advances every shot of the batch by one step
+        if adj > 0 and fwd > 0:
+            dom_name, dom_ms, dom_bytes = (("adjoint step (elf_k1 + elf_k2)", adj, B_EL_ADJ) if adj >= fwd else
+                                           ("forward step, recording (elf_s + elf_v)", fwd, B_EL_FWD_SAVE))
+            ach = dom_bytes * cells / (dom_ms * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath):
+                try:
+                    tj = json.load(open(tpath)).get(args.workload, {})
+                    if tj.get("batch") == batch:
+                        traffic = tj.get("el_adj" if adj >= fwd else "el_fwd")
+                except Exception:
+                    traffic = None
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "kernel": dom_name, "avg_launch_ms": dom_ms, "algorithmic_bytes_per_cell_update": dom_bytes,
+                    "cells_per_launch": cells, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                    "whole_step_frac": B_EL_GRAD_STEP / 2 * value * 1e9 / world / (peak * 1e9),
+                    "note": "the step = two launches (stress, velocity); the timed region also holds the recomputation sweep of the "
+                            "checkpointed segments, which is overhead, not counted work",
+                    "per_kernel_avg_ms": avg}
+        cns, cnt = cpu_sample_size()
+        cpu_v, cpu_s = cpu_gradient_sample(wl, cns, cnt)
+        line = {
+            "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": value, "unit": "Gcell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "shots_per_gpu": ns_local, "shots_total": ns_total,
+                       "batch_size": batch, "padded_grid": [nzp, nxp], "nt": nt, "receivers": wl["nr"], "gradients": list(grads),
+                       "l2": "working set per step >> 126 MB L2 (inputs larger than L2; no explicit flush)",
+                       "parallelism": f"shots sharded over {world} GPU(s), one all-reduce of the gradients"},
+            "shots_per_s": ns_total * args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(lt.item()), "roofline": roof,
+            "cpu_baseline": {"value": cpu_v / 1e9, "unit": "Gcell-updates/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"oracle/ C port (OpenMP, all host threads), {cns} shots x {cnt} steps of the {args.workload} grid, "
+                                       f"forward+adjoint, {cpu_s:.1f} s"},
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -341,11 +560,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--shots", type=int, default=0, help="shots per GPU (default: the workload's share of an 8-GPU job)")
+    ap.add_argument("--batch", type=int, default=0, help="shots per propagator call (default: the workload's)")
+    ap.add_argument("--nt", type=int, default=0, help="time steps (default: the workload's; shorter = a slice, labelled in config.nt)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("kind") == "elastic":
+        run_b200_elastic(args, wl)
     else:
         run_b200(args, wl)
 
