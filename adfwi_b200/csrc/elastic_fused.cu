@@ -56,13 +56,23 @@ template <int NN> struct Geo {
     static constexpr int V_STAGE = 3 * HB + 4 * CB;
     static constexpr int K1_STAGE = 6 * HB;
     static constexpr int K2_STAGE = 9 * HB;
+    // fused forward kernel: velocity splits staged with a halo of 2NN (the stress is recomputed on a ring of NN)
+    static constexpr int HX2 = NN == 2 ? 4 : 8;
+    static constexpr int RX2 = TX + 2 * HX2;
+    static constexpr int RZ2 = TZ + 4 * NN;
+    static constexpr int HF2 = RZ2 * RX2;
+    static constexpr int HB2 = (HF2 * 4 + 127) / 128 * 128;
+    static constexpr int F_VSTAGE = 4 * HB2;                   // double-buffered
+    static constexpr int F_SMEM = NSTAGE * F_VSTAGE + 6 * HB + 3 * HB;   // + stress splits (single buffer) + stress sums
 };
 constexpr int TAIL_BYTES = 64 + 2 * CMAX * 4 + 3 * CMAX * 4 + 64;   // elf_s: mbarriers + per-shot scalars
 constexpr int TAIL_SMALL = 64 + 2 * CMAX * 4;                       // other kernels: mbarriers + source cells
 
 // plane index of field f, shot s in the workspace's plane array: f*ns + s
 enum { P_VXX = 0, P_VXZ, P_VZX, P_VZZ, P_S0, P_S1, P_S2, P_S3, P_S4, P_S5, P_TXX, P_TZZ, P_TXZ, P_FWD_COUNT,
-       P_LV = P_FWD_COUNT,          // 2 x 4 velocity-split cotangents (ping-pong)
+       P_B0 = P_FWD_COUNT,          // second set of the 10 split fields (ping-pong of the fused forward kernel elf_f)
+       P_FWD2_COUNT = P_B0 + 10,
+       P_LV = P_FWD2_COUNT,         // 2 x 4 velocity-split cotangents (ping-pong)
        P_LS = P_LV + 8,             // 2 x 6 stress-split cotangents (ping-pong)
        P_LVX = P_LS + 12, P_LVZ,    // cotangents of the velocity sums
        P_MXX, P_MZZ, P_MXZ,         // cotangents of the stress sums (between elf_k1 and elf_k2)
@@ -269,6 +279,11 @@ struct Cursor {
             ring[wr++ & 3u] = it;
             set(it, g, w);
         }
+    }
+    // a second producer cursor that trails the drawing one reads the ids from the ring (wr is its read index)
+    __device__ __forceinline__ void next_follow(const EGeom& g, const Walk& w, const int* ring)
+    {
+        if (valid && ++s >= s_hi) set(ring[wr++ & 3u], g, w);
     }
 };
 
@@ -660,6 +675,339 @@ elf_v(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
         if (a.tflags[tile]) v_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
         else                v_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
+        __syncthreads();
+    }
+}
+
+
+// ==========================================================================================
+// elf_f : fused forward step = elf_s + elf_v in one launch (:341-409 / :497-565)
+//
+// The stress update is recomputed on a ring of NN cells around the tile, so the velocity update of the tile
+// finds every stress sum it needs in shared memory: the sums never travel to HBM and the velocity splits are
+// read once.  Per shot the 4 velocity splits (halo 2NN, double-buffered stage) and the 6 stress splits
+// (tile + ring, single buffer refilled as soon as phase A has consumed it) arrive by TMA; all ten split fields are
+// written to the other set of a ping-pong pair (neighbouring tiles still read the old values of the ring).
+// HBM traffic per cell-update: 10 fields read + 10 written (+ 8 history planes in recording mode).
+// ==========================================================================================
+struct FArgs { ECoef cp; const unsigned char* tflags; float* planes; int cur; const float* mt; const float* src_v;
+               const int64_t *sx, *sz; float* hist; int hist_len, tl, it; int nr; RcvB rb; float* rcv[5]; Walk w; };
+
+template <int NN> __device__ __forceinline__ void f_issue_v(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
+                                                            const CUtensorMap* th2, int ns, int base)
+{
+    using G = Geo<NN>;
+    unsigned char* st = smem + k * G::F_VSTAGE;
+    fence_proxy_async();
+    mbar_expect_tx(bar + k, 4 * G::HF2 * 4);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) tma_load_3d(st + f * G::HB2, th2, c.X0 - G::HX2, c.Z0 - 2 * NN, (base + P_VXX + f) * ns + c.s, bar + k);
+}
+template <int NN> __device__ __forceinline__ void f_issue_s(const Cursor& c, unsigned char* sst, uint64_t* bar,
+                                                            const CUtensorMap* th, int ns, int base)
+{
+    using G = Geo<NN>;
+    fence_proxy_async();
+    mbar_expect_tx(bar, 6 * G::HF * 4);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) tma_load_3d(sst + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (base + P_S0 + f) * ns + c.s, bar);
+}
+
+// stress update of one float4 group.  hv = index of the group in the velocity rects (pitch RX2), a[6] = the
+// split stresses of the group (in: old, out: new where the mask is set), d[4] = D-x vx, D-z vz, D+x vz, D+z vx
+template <int NN, bool PML>
+__device__ __forceinline__ void f_stress_cell(const EGeom& g, unsigned m, const float* vxx, const float* vxz, const float* vzx, const float* vzz,
+                                              int hv, float4* a, const float4& c11, const float4& c13, const float4& c33, const float4& c55,
+                                              const float4& pxn, const float4& pxi, const float4& pzn, const float4& pzi, float4* d)
+{
+    constexpr int RX2 = Geo<NN>::RX2;
+    float sx_[12], sz_[12];
+    ldseg2(vxx + hv, vxz + hv, sx_);
+    ldseg2(vzx + hv, vzz + hv, sz_);
+    float4 wzb[2 * NN], wzf[2 * NN];
+#pragma unroll
+    for (int q = 0; q < 2 * NN; ++q) {
+        wzb[q] = add4(ld4(vzx + hv + (q - NN) * RX2), ld4(vzz + hv + (q - NN) * RX2));
+        wzf[q] = add4(ld4(vxx + hv + (q - NN + 1) * RX2), ld4(vxz + hv + (q - NN + 1) * RX2));
+    }
+    d[0] = xdiff<NN, 0>(sx_, g.c); d[2] = xdiff<NN, 1>(sz_, g.c);
+    d[1] = zdiff<NN>(wzb, g.c); d[3] = zdiff<NN>(wzf, g.c);
+    float4 n0, n1, n2, n3, n4, n5;
+    if (PML) {
+        n0 = mul4(add4(mul4(pxn, a[0]), smul(g.dt_dx, mul4(c11, d[0]))), pxi);
+        n1 = mul4(add4(mul4(pzn, a[1]), smul(g.dt_dz, mul4(c13, d[1]))), pzi);
+        n2 = mul4(add4(mul4(pxn, a[2]), smul(g.dt_dx, mul4(c13, d[0]))), pxi);
+        n3 = mul4(add4(mul4(pzn, a[3]), smul(g.dt_dz, mul4(c33, d[1]))), pzi);
+        n4 = mul4(add4(mul4(pxn, a[4]), smul(g.dt_dx, mul4(c55, d[2]))), pxi);
+        n5 = mul4(add4(mul4(pzn, a[5]), smul(g.dt_dz, mul4(c55, d[3]))), pzi);
+    } else {
+        n0 = add4(a[0], smul(g.dt_dx, mul4(c11, d[0])));
+        n1 = add4(a[1], smul(g.dt_dz, mul4(c13, d[1])));
+        n2 = add4(a[2], smul(g.dt_dx, mul4(c13, d[0])));
+        n3 = add4(a[3], smul(g.dt_dz, mul4(c33, d[1])));
+        n4 = add4(a[4], smul(g.dt_dx, mul4(c55, d[2])));
+        n5 = add4(a[5], smul(g.dt_dz, mul4(c55, d[3])));
+    }
+    a[0] = sel4(m, n0, a[0]); a[1] = sel4(m, n1, a[1]); a[2] = sel4(m, n2, a[2]);
+    a[3] = sel4(m, n3, a[3]); a[4] = sel4(m, n4, a[4]); a[5] = sel4(m, n5, a[5]);
+}
+
+template <int NN, bool PML, bool FS, bool SAVE>
+__device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap* th2, const EGeom& g, const FArgs& a,
+                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pcv, Cursor& pcs, int* ring,
+                                       int* s_sz, int* s_sx, float* s_sxx, float* s_szz, float* s_sxz,
+                                       const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
+{
+    using G = Geo<NN>;
+    constexpr int RX2 = G::RX2, HX2 = G::HX2, HQ = G::HB / 4, HQ2 = G::HB2 / 4;
+    const uint64_t pol = l2_keep_policy();
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
+    const unsigned cm = col_mask<NN>(gx, g.nxp);
+    const bool col_ok = gx < g.ld;
+    const size_t fp = (size_t)g.ns * g.plane;
+    const int rbase = a.cur ? P_B0 : 0, wbase = a.cur ? 0 : P_B0;
+    unsigned char* sst = smem + NSTAGE * G::F_VSTAGE;
+    float* ssp = (float*)sst;                               // 6 stress-split rects (tile + ring)
+    float* sum = (float*)(sst + 6 * G::HB);                 // 3 stress-sum rects (tile + ring)
+    float* txx = sum; float* tzz = sum + HQ; float* txz = sum + 2 * HQ;
+    if (tid < s_hi - s_lo) {
+        const int s = s_lo + tid;
+        const float* M = a.mt + (size_t)s * 9;
+        const float v = a.src_v[(size_t)s * g.nt + a.it];
+        s_sz[tid] = (int)a.sz[s]; s_sx[tid] = (int)a.sx[s];
+        s_sxx[tid] = (-(M[0] / 2.0f)) * v; s_szz[tid] = (-(M[8] / 2.0f)) * v; s_sxz[tid] = (-(M[2] / 2.0f)) * v;
+    }
+    float4 C11[RPT], C13[RPT], C33[RPT], C55[RPT], DBX[RPT], DBZ[RPT], PXN[RPT], PZN[RPT], PXD[RPT], PZD[RPT], PXI[RPT], PZI[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
+        C11[j] = ldk4(a.cp.c11 + o, pol); C13[j] = ldk4(a.cp.c13 + o, pol);
+        C33[j] = ldk4(a.cp.c33 + o, pol); C55[j] = ldk4(a.cp.c55 + o, pol);
+        DBX[j] = smul(g.dt, ldk4(a.cp.bx + o, pol)); DBZ[j] = smul(g.dt, ldk4(a.cp.bz + o, pol));
+        if (PML) {
+            const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+            PXD[j] = add4(one4(), smul(g.half_dt, bx_)); PZD[j] = add4(one4(), smul(g.half_dt, bz_));
+            PXN[j] = sub4(one4(), smul(g.half_dt, bx_)); PZN[j] = sub4(one4(), smul(g.half_dt, bz_));
+            PXI[j] = div4(one4(), PXD[j]); PZI[j] = div4(one4(), PZD[j]);
+        } else { PXD[j] = PZD[j] = PXN[j] = PZN[j] = PXI[j] = PZI[j] = one4(); }
+    }
+    const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
+    const bool has_rcv = rcv_hi > rcv_lo;
+    if (first) {
+        griddep_wait();
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < NSTAGE; ++k)
+                if (pcv.valid) { f_issue_v<NN>(pcv, smem, bar, k, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
+            if (pcs.valid) { f_issue_s<NN>(pcs, sst, bar + NSTAGE, th, g.ns, rbase); pcs.next_follow(g, a.w, ring); }
+        }
+    }
+    __syncthreads();
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int k = stage;
+        float* vxx = (float*)(smem + k * G::F_VSTAGE); float* vxz = vxx + HQ2; float* vzx = vxx + 2 * HQ2; float* vzz = vxx + 3 * HQ2;
+        const int szs = s_sz[s - s_lo], sxs = s_sx[s - s_lo];
+        const float sxx = s_sxx[s - s_lo], szz = s_szz[s - s_lo], sxz = s_sxz[s - s_lo];
+        ELF_WAIT_STAGE(k);
+        if (FS && tzi == 0) {          // free-surface velocity rows (:399-402) formed in the staged rects (see elf_s)
+            const int t = tid;
+            if (t >= HX2 - NN && t < HX2 + TX + NN) {
+                const int j = X0 + t - HX2;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (3 * NN) * RX2 + t, rh = (3 * NN + 1) * RX2 + t, rh2 = (3 * NN - 1) * RX2 + t, rh3 = (3 * NN - 2) * RX2 + t;
+                    const float vz1 = vzx[rh1] + vzz[rh1];
+                    const float vz1n = (j + 1 < g.nxp - NN) ? vzx[rh1 + 1] + vzz[rh1 + 1] : 0.f;
+                    const float vxh = vxx[rh] + vxz[rh];
+                    const float nvx = (((vz1n - vz1) + vz1n) - vz1) + vxh;
+                    vzx[rh2] = vz1; vzz[rh2] = 0.f; vzx[rh3] = vz1; vzz[rh3] = 0.f;
+                    vxx[rh2] = nvx; vxz[rh2] = 0.f;
+                }
+            }
+            __syncthreads();
+        }
+        ELF_WAIT_STAGE(NSTAGE);
+        // ---- phase A: stress on the tile (coefficients in registers) and on the ring (coefficients from L2) ----
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = R.r0 + j, gz = gz0 + j;
+            const int hv = (r + 2 * NN) * RX2 + R.c0 + HX2, hs = (r + NN) * RXH + R.c0 + HX;
+            const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
+            float4 sp[6], d[4];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) sp[f] = ld4(ssp + f * HQ + hs);
+            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, sp, C11[j], C13[j], C33[j], C55[j], PXN[j], PXI[j], PZN[j], PZI[j], d);
+            if (szs == gz && !(FS && gz < NN)) {
+                const int dc = sxs - gx;
+                if (dc >= 0 && dc < 4) { addc4(sp[0], dc, sxx); addc4(sp[1], dc, sxx); addc4(sp[2], dc, szz); addc4(sp[3], dc, szz); addc4(sp[4], dc, sxz); addc4(sp[5], dc, sxz); }
+            }
+            st4(txx + hs, add4(sp[0], sp[1])); st4(tzz + hs, add4(sp[2], sp[3])); st4(txz + hs, add4(sp[4], sp[5]));
+            if (col_ok && gz < g.nzp) {
+                const size_t o = (size_t)gz * g.ld + gx;
+                float* P = a.planes + (size_t)s * g.plane + o + (size_t)(wbase + P_S0) * fp;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) st4(P + f * fp, sp[f]);
+                if (SAVE) {
+                    float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + o;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(H + (size_t)e * g.plane), sel4(m, d[e], zero4()));
+                }
+            }
+        }
+        for (int i = tid; i < G::NRING; i += NTH) {
+            int r, gi;
+            ring_cell<NN>(i, r, gi);
+            const int gzr = Z0 + r, gxr = X0 + 4 * gi;
+            const int hv = (r + 2 * NN) * RX2 + 4 * gi + HX2, hs = (r + NN) * RXH + 4 * gi + HX;
+            const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
+            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
+            float4 pxn = one4(), pxi = one4(), pzn = one4(), pzi = one4();
+            if (PML) {
+                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
+                pxi = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); pzi = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+            }
+            float4 sp[6], d[4];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) sp[f] = ld4(ssp + f * HQ + hs);
+            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol),
+                                   ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, d);
+            if (szs == gzr && !(FS && gzr < NN)) {
+                const int dc = sxs - gxr;
+                if (dc >= 0 && dc < 4) { addc4(sp[0], dc, sxx); addc4(sp[1], dc, sxx); addc4(sp[2], dc, szz); addc4(sp[3], dc, szz); addc4(sp[4], dc, sxz); addc4(sp[5], dc, sxz); }
+            }
+            st4(txx + hs, add4(sp[0], sp[1])); st4(tzz + hs, add4(sp[2], sp[3])); st4(txz + hs, add4(sp[4], sp[5]));
+        }
+        __syncthreads();
+        // the stress-split buffer has been consumed: refill it with the next shot while phase B runs
+        if (tid == 0 && pcs.valid) { f_issue_s<NN>(pcs, sst, bar + NSTAGE, th, g.ns, rbase); pcs.next_follow(g, a.w, ring); }
+        if (FS && tzi == 0) {          // free-surface stress rows (:380-384) on the sums
+            const int t = tid;
+            if (t < RXH) {
+                const int j = X0 + t - HX;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (2 * NN) * RXH + t, rh = (2 * NN + 1) * RXH + t, rh2 = (2 * NN - 1) * RXH + t, rh3 = (2 * NN - 2) * RXH + t;
+                    tzz[rh1] = 0.f;
+                    txz[rh2] = -txz[rh1];
+                    tzz[rh2] = -tzz[rh];
+                    txz[rh3] = -txz[rh];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase B: velocity on the tile, history, receivers ------------------------------------------
+        float4 nvx[RPT], nvz[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int r = R.r0 + j, gz = gz0 + j;
+            const int hv = (r + 2 * NN) * RX2 + R.c0 + HX2, hs = (r + NN) * RXH + R.c0 + HX;
+            float sxx_[12], sxz_[12];
+            ldseg(txx + hs, sxx_);
+            ldseg(txz + hs, sxz_);
+            float4 wzb[2 * NN], wzf[2 * NN];
+#pragma unroll
+            for (int q = 0; q < 2 * NN; ++q) {
+                wzb[q] = ld4(txz + hs + (q - NN) * RXH);
+                wzf[q] = ld4(tzz + hs + (q - NN + 1) * RXH);
+            }
+            const float4 dxf_txx = xdiff<NN, 1>(sxx_, g.c), dxb_txz = xdiff<NN, 0>(sxz_, g.c);
+            const float4 dzb_txz = zdiff<NN>(wzb, g.c), dzf_tzz = zdiff<NN>(wzf, g.c);
+            float4 q0 = ld4(vxx + hv), q1 = ld4(vxz + hv), q2 = ld4(vzx + hv), q3 = ld4(vzz + hv);
+            const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
+            float4 n0, n1, n2, n3;
+            {
+                const float4 A0 = mul4(DBX[j], dxf_txx), A1 = mul4(DBX[j], dzb_txz), A2 = mul4(DBZ[j], dxb_txz), A3 = mul4(DBZ[j], dzf_tzz);
+                DivGuard dg;
+                dg.add(A0); dg.add(A1); dg.add(A2); dg.add(A3);
+                float4 t0 = fdivs(A0, g.dx, g.rdx), t1 = fdivs(A1, g.dz, g.rdz), t2 = fdivs(A2, g.dx, g.rdx), t3 = fdivs(A3, g.dz, g.rdz);
+                if (PML) {
+                    const float4 B0 = add4(mul4(PXN[j], q0), t0), B1 = add4(mul4(PZN[j], q1), t1);
+                    const float4 B2 = add4(mul4(PXN[j], q2), t2), B3 = add4(mul4(PZN[j], q3), t3);
+                    dg.add(B0); dg.add(B1); dg.add(B2); dg.add(B3);
+                    n0 = fdiv4(B0, PXD[j], PXI[j]); n1 = fdiv4(B1, PZD[j], PZI[j]); n2 = fdiv4(B2, PXD[j], PXI[j]); n3 = fdiv4(B3, PZD[j], PZI[j]);
+                } else {
+                    n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
+                }
+                if (!dg.ok()) {
+                    t0 = ieee_divs(A0, g.dx); t1 = ieee_divs(A1, g.dz); t2 = ieee_divs(A2, g.dx); t3 = ieee_divs(A3, g.dz);
+                    if (PML) {
+                        n0 = ieee_div4(add4(mul4(PXN[j], q0), t0), PXD[j]); n1 = ieee_div4(add4(mul4(PZN[j], q1), t1), PZD[j]);
+                        n2 = ieee_div4(add4(mul4(PXN[j], q2), t2), PXD[j]); n3 = ieee_div4(add4(mul4(PZN[j], q3), t3), PZD[j]);
+                    } else {
+                        n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
+                    }
+                }
+            }
+            q0 = sel4(m, n0, q0); q1 = sel4(m, n1, q1); q2 = sel4(m, n2, q2); q3 = sel4(m, n3, q3);
+            nvx[j] = add4(q0, q1); nvz[j] = add4(q2, q3);
+            if (col_ok && gz < g.nzp) {
+                const size_t o = (size_t)gz * g.ld + gx;
+                float* P = a.planes + (size_t)s * g.plane + o + (size_t)(wbase + P_VXX) * fp;
+                st4(P, q0); st4(P + fp, q1); st4(P + 2 * fp, q2); st4(P + 3 * fp, q3);
+                if (SAVE) {
+                    float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + o;
+                    __stcs(reinterpret_cast<float4*>(H), sel4(m, dxf_txx, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_txz, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxb_txz, zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_tzz, zero4()));
+                }
+            }
+        }
+        if (has_rcv) {                 // receivers of this tile (:405-409): new sums parked in the vxx / vzx rects
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) { const int hv = (R.r0 + j + 2 * NN) * RX2 + R.c0 + HX2; st4(vxx + hv, nvx[j]); st4(vzx + hv, nvz[j]); }
+            __syncthreads();
+            for (int i = rcv_lo + tid; i < rcv_hi; i += NTH) {
+                const int r = a.rb.id[i], zx = a.rb.zx[i];
+                const int z = (zx >> 16) - Z0, x = (zx & 0xffff) - X0;
+                const int oh = (z + NN) * RXH + x + HX, ov = (z + 2 * NN) * RX2 + x + HX2;
+                const size_t o = ((size_t)s * g.nt + a.it) * a.nr + r;
+                a.rcv[0][o] = txx[oh]; a.rcv[1][o] = tzz[oh]; a.rcv[2][o] = txz[oh];
+                a.rcv[3][o] = vxx[ov]; a.rcv[4][o] = vzx[ov];
+            }
+        }
+        if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
+        __syncthreads();
+        if (tid == 0 && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, k, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
+        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+    }
+}
+
+template <int NN, bool FS, bool SAVE>
+__global__ void __launch_bounds__(NTH, 2)
+elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap th2, const EGeom g, const FArgs a)
+{
+    using G = Geo<NN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = (uint64_t*)(smem + G::F_SMEM);
+    int* s_sz = (int*)(bar + 8);
+    int* s_sx = s_sz + CMAX;
+    float* s_sxx = (float*)(s_sx + CMAX);
+    float* s_szz = s_sxx + CMAX;
+    float* s_sxz = s_szz + CMAX;
+    const int tid = threadIdx.x;
+    if (tid == 0) { for (int k = 0; k < NSTAGE + 1; ++k) mbar_init(bar + k, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    int stage = 0;
+    const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    int* ring = (int*)(bar + 4);
+    Cursor pcv, pcs;
+    pcv.wr = 0; pcs.wr = 0;
+    pcv.set(blockIdx.x, g, a.w);
+    pcs.set(blockIdx.x, g, a.w);
+    griddep_launch_dependents();
+    unsigned rd = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < nitems; item = ring[rd++ & 3u], first = false) {
+        const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
+        const int s_lo = a.w.s_begin + chunk * a.w.chunk;
+        const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
+        if (a.tflags[tile]) f_tile<NN, true, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        else                f_tile<NN, false, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -1243,7 +1591,7 @@ __global__ void elf_reduce_parts(int nzp, int nxp, int ld, size_t plane, int npa
 }
 
 // squares of the five sum fields of the current state, summed over shots (:414-418), physical cells only
-__global__ void elf_illum_acc(EGeom g, int NN, int nz, int nx, int nabc, int zoff, int sb, int se, const float* __restrict__ planes, float* __restrict__ ill)
+__global__ void elf_illum_acc(EGeom g, int NN, int nz, int nx, int nabc, int zoff, int sb, int se, int base, const float* __restrict__ planes, float* __restrict__ ill)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
     if (x >= nx || z >= nz) return;
@@ -1252,8 +1600,8 @@ __global__ void elf_illum_acc(EGeom g, int NN, int nz, int nx, int nabc, int zof
     const size_t fp = (size_t)g.ns * g.plane;
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = sb; s < se; ++s) {
-        const float* P = planes + (size_t)s * g.plane + c;
-        float txx = P[P_TXX * fp], tzz = P[P_TZZ * fp], txz = P[P_TXZ * fp];
+        const float* P = planes + (size_t)s * g.plane + c + (size_t)base * fp;
+        float txx = P[P_S0 * fp] + P[P_S1 * fp], tzz = P[P_S2 * fp] + P[P_S3 * fp], txz = P[P_S4 * fp] + P[P_S5 * fp];
         if (g.fs && gz == NN) tzz = 0.f;                        // tzz[h-1] = 0 (:380)
         const float vx = P[P_VXX * fp] + P[P_VXZ * fp], vz = P[P_VZX * fp] + P[P_VZZ * fp];
         acc[0] += txx * txx; acc[1] += tzz * tzz; acc[2] += txz * txz; acc[3] += vx * vx; acc[4] += vz * vz;
@@ -1325,7 +1673,7 @@ int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
     const size_t sp = (size_t)d->ns * g.plane;
     P->pack = cv.take<float>(8 * P->cpplane);
     P->tflags = cv.take<unsigned char>(ntiles);
-    P->nfields = P->save ? P_COUNT : P_FWD_COUNT;
+    P->nfields = P->save ? P_COUNT : P_FWD2_COUNT;
     P->planes = cv.take<float>((size_t)P->nfields * sp);
     P->ill = cv.take<float>((size_t)5 * d->nz * d->nx);
     P->rcv_cnt = cv.take<int>(ntiles + 1); P->rcv_start = cv.take<int>(ntiles + 1); P->rcv_cursor = cv.take<int>(ntiles + 1);
@@ -1380,7 +1728,7 @@ int elf_setup(const EFPlan& P, cudaStream_t st, const float* const* coef, const 
     return ADFWI_OK;
 }
 
-struct EMaps { CUtensorMap halo, core, hist; };
+struct EMaps { CUtensorMap halo, halo2, core, hist; };
 
 int elf_make_maps(const EFPlan& P, EMaps* M)
 {
@@ -1388,6 +1736,8 @@ int elf_make_maps(const EFPlan& P, EMaps* M)
     int rc = make_tmap_f32(&M->halo, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, RXH, TZ + 2 * P.NN);
     if (rc) return rc;
     rc = make_tmap_f32(&M->core, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, TX, TZ);
+    if (rc) return rc;
+    rc = make_tmap_f32(&M->halo2, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, TX + 2 * (P.NN == 2 ? 4 : 8), TZ + 4 * P.NN);
     if (rc || !P.save) return rc;
     return make_tmap_f32(&M->hist, P.hist, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.ns * P.K * NHIST, TX, TZ);
 }
@@ -1413,9 +1763,11 @@ template <typename K> int elf_set_smem(K kern, int bytes) { return (int)cudaFunc
 
 template <int NN> constexpr int s_smem() { return NSTAGE * Geo<NN>::S_STAGE + TAIL_BYTES; }
 template <int NN> constexpr int v_smem() { return NSTAGE * Geo<NN>::V_STAGE + TAIL_SMALL; }
+template <int NN> constexpr int f_smem() { return Geo<NN>::F_SMEM + TAIL_BYTES; }
 template <int NN> constexpr int k1_smem() { return NSTAGE * Geo<NN>::K1_STAGE + TAIL_SMALL; }
 template <int NN> constexpr int k2_smem() { return NSTAGE * Geo<NN>::K2_STAGE + TAIL_SMALL; }
-static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472, "two CTAs per SM must fit in shared memory");
+static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472 && 2 * (f_smem<2>() + 1024) <= 233472 && f_smem<3>() <= 232448,
+              "two CTAs per SM must fit in shared memory (the O(2,6) fused forward kernel runs one CTA per SM)");
 
 template <int NN> int elf_init_kernels()
 {
@@ -1426,6 +1778,8 @@ template <int NN> int elf_init_kernels()
     rc |= elf_set_smem(elf_s<NN, false, true>, s_smem<NN>());  rc |= elf_set_smem(elf_s<NN, false, false>, s_smem<NN>());
     rc |= elf_set_smem(elf_v<NN, true, true>, v_smem<NN>());   rc |= elf_set_smem(elf_v<NN, true, false>, v_smem<NN>());
     rc |= elf_set_smem(elf_v<NN, false, true>, v_smem<NN>());  rc |= elf_set_smem(elf_v<NN, false, false>, v_smem<NN>());
+    rc |= elf_set_smem(elf_f<NN, true, true>, f_smem<NN>());   rc |= elf_set_smem(elf_f<NN, true, false>, f_smem<NN>());
+    rc |= elf_set_smem(elf_f<NN, false, true>, f_smem<NN>());  rc |= elf_set_smem(elf_f<NN, false, false>, f_smem<NN>());
     rc |= elf_set_smem(elf_k1<NN, true>, k1_smem<NN>());       rc |= elf_set_smem(elf_k1<NN, false>, k1_smem<NN>());
     rc |= elf_set_smem(elf_k2<NN, true>, k2_smem<NN>());       rc |= elf_set_smem(elf_k2<NN, false>, k2_smem<NN>());
     if (!rc) done = true;
@@ -1443,16 +1797,42 @@ inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid)
 
 struct EArgs { const float *mt, *src_v; const int64_t *sx, *sz; };
 
-// one forward step of shots [sb,se): elf_s then elf_v
+inline bool elf_split_forward()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_EL_SPLIT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v != 0;
+}
+
+// one forward step of shots [sb,se).  Default: the fused kernel elf_f (reads split-field set *cur, writes the other
+// one and flips *cur).  ADFWI_B200_EL_SPLIT=1 selects the two-launch form elf_s + elf_v (in place on set 0).
 template <int NN>
 int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, int se, int it, bool save, int tl,
-                     const EArgs& ea, float* const* rcv, int* seq)
+                     const EArgs& ea, float* const* rcv, int* seq, int* cur)
 {
     if (*seq + 2 > P.ncounters) return ADFWI_E_DIMS;
     const EGeom& g = P.g;
     int grid;
     const Walk w = elf_walk(P, sb, se, &grid);
     const bool pdl = elf_use_pdl();
+    if (!elf_split_forward()) {
+        FArgs a;
+        a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.cur = *cur; a.mt = ea.mt; a.src_v = ea.src_v; a.sx = ea.sx; a.sz = ea.sz;
+        a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it;
+        a.nr = rcv ? P.nr : 0; a.rb = elf_bucket_ptrs(P);
+        for (int k = 0; k < 5; ++k) a.rcv[k] = rcv ? rcv[k] : nullptr;
+        a.w = w; a.w.counter = P.counters + (*seq)++;
+        {
+            TimedLaunch tl_(KC_EL_FWD_STRESS, st);
+            if (P.FS) { if (save) ADFWI_CUDA(elf_launch(elf_f<NN, true, true>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a));
+                        else      ADFWI_CUDA(elf_launch(elf_f<NN, true, false>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a)); }
+            else      { if (save) ADFWI_CUDA(elf_launch(elf_f<NN, false, true>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a));
+                        else      ADFWI_CUDA(elf_launch(elf_f<NN, false, false>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a)); }
+        }
+        ADFWI_LAUNCH_CHECK();
+        *cur ^= 1;
+        return ADFWI_OK;
+    }
     {
         SArgs a;
         a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.mt = ea.mt; a.src_v = ea.src_v; a.sx = ea.sx; a.sz = ea.sz;
@@ -1481,12 +1861,12 @@ int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, i
 }
 
 // the 10 persistent split fields of shots [sb,se) <-> checkpoint slot
-int elf_copy_state(const EFPlan& P, cudaStream_t st, int sb, int se, float* ck, bool to_ckpt)
+int elf_copy_state(const EFPlan& P, cudaStream_t st, int sb, int se, float* ck, bool to_ckpt, int cur)
 {
     const size_t sp = (size_t)P.ns * P.g.plane;
     const size_t off = (size_t)sb * P.g.plane, cnt = (size_t)(se - sb) * P.g.plane * sizeof(float);
     for (int f = 0; f < 10; ++f) {
-        float* a = P.planes + (size_t)f * sp + off;
+        float* a = P.planes + (size_t)((cur ? P_B0 : 0) + f) * sp + off;
         float* b = ck + (size_t)f * sp + off;
         ADFWI_CUDA(cudaMemcpyAsync(to_ckpt ? b : a, to_ckpt ? a : b, cnt, cudaMemcpyDeviceToDevice, st));
     }
@@ -1513,19 +1893,20 @@ int elf_forward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs&
     int seq = 0;
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
-        int rc = elf_zero_fields(P, st, 0, P_FWD_COUNT, sb, se);
+        int rc = elf_zero_fields(P, st, 0, P_FWD2_COUNT, sb, se);
         if (rc) return rc;
+        int cur = 0;
         for (int it = 0; it < nt; ++it) {
             const int seg = it / P.K, tl = it - seg * P.K;
             if (P.save && tl == 0 && seg >= 1 && seg <= P.nseg - 2) {
-                rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, true);
+                rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, true, cur);
                 if (rc) return rc;
             }
             const bool save = P.save && seg == P.nseg - 1;
-            rc = elf_forward_step<NN>(P, M, st, sb, se, it, save, tl, ea, P.nr > 0 ? rcv : nullptr, &seq);
+            rc = elf_forward_step<NN>(P, M, st, sb, se, it, save, tl, ea, P.nr > 0 ? rcv : nullptr, &seq, &cur);
             if (rc) return rc;
             if (illum && ((it + 1) % csz == 0 || it == nt - 1)) {
-                elf_illum_acc<<<dim3(cdiv(P.nx, 128), P.nz), 128, 0, st>>>(g, NN, P.nz, P.nx, P.nabc, P.zoff, sb, se, P.planes, P.ill);
+                elf_illum_acc<<<dim3(cdiv(P.nx, 128), P.nz), 128, 0, st>>>(g, NN, P.nz, P.nx, P.nabc, P.zoff, sb, se, cur ? P_B0 : 0, P.planes, P.ill);
                 ADFWI_LAUNCH_CHECK();
             }
         }
@@ -1556,11 +1937,12 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
         for (int seg = P.nseg - 1; seg >= 0; --seg) {
             const int t0 = seg * P.K, t1 = t0 + P.K < nt ? t0 + P.K : nt;
             if (seg != P.nseg - 1) {
-                if (seg == 0) rc = elf_zero_fields(P, st, 0, P_FWD_COUNT, sb, se);
-                else          rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, false);
+                int cur = 0;
+                if (seg == 0) rc = elf_zero_fields(P, st, 0, P_FWD2_COUNT, sb, se);
+                else          rc = elf_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * 10 * P.ns * g.plane, false, 0);
                 if (rc) return rc;
                 for (int it = t0; it < t1; ++it) {
-                    rc = elf_forward_step<NN>(P, M, st, sb, se, it, true, it - t0, ea, nullptr, &seq);
+                    rc = elf_forward_step<NN>(P, M, st, sb, se, it, true, it - t0, ea, nullptr, &seq, &cur);
                     if (rc) return rc;
                 }
             }
