@@ -81,6 +81,7 @@ constexpr int NHIST = 8;            // history planes per step: dxb_vx, dzb_vz, 
 
 struct EGeom {
     int nzp, nxp, ld, fs, nt, ns, ntx, ntz, cpld;
+    int merge;               // 1: lean adjoint for damping-free tiles (tile classes 0/2, see elf_tile_class)
     size_t plane;
     float dt, dx, dz, dt_dx, dt_dz, half_dt;
     float rdx, rdz;          // RN(1/dx), RN(1/dz) for fdivs()
@@ -261,12 +262,13 @@ template <int NN> __device__ __forceinline__ float4 zgath(const float4* w, const
 // ragged chunks cost differently).  Only thread 0 -- the TMA producer, running NSTAGE shots ahead of the compute --
 // keeps a cursor; the ids it draws are handed to the consumers through a 4-entry ring in shared memory.
 struct Cursor {
-    int item, s, s_hi, X0, Z0; bool valid; unsigned wr;
+    int item, tile, s, s_hi, X0, Z0; bool valid; unsigned wr;
     __device__ __forceinline__ void set(int it, const EGeom& g, const Walk& w)
     {
         item = it; valid = it < g.ntx * g.ntz * w.nchunks;
         if (valid) {
-            const int tile = it / w.nchunks, ch = it - tile * w.nchunks;
+            tile = it / w.nchunks;
+            const int ch = it - tile * w.nchunks;
             const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
             X0 = txi * TX; Z0 = tzi * TZ;
             s = w.s_begin + ch * w.chunk; s_hi = min(s + w.chunk, w.s_end);
@@ -341,6 +343,7 @@ __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap*
     const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
     const unsigned cm = col_mask<NN>(gx, g.nxp);
     const bool col_ok = gx < g.ld;
+    const bool lean = !PML && g.merge;     // merged history planes for damping-free tiles (see k1_tile / k2_tile)
     if (tid < s_hi - s_lo) {         // per-shot scalars (:341-346: -(M/2)*src)
         const int s = s_lo + tid;
         const float* M = a.mt + (size_t)s * 9;
@@ -452,8 +455,11 @@ __device__ __forceinline__ void s_tile(const CUtensorMap* th, const CUtensorMap*
                     float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + o;
                     __stcs(reinterpret_cast<float4*>(H), sel4(m, dxb_vx, zero4()));
                     __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_vz, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxf_vz, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_vx, zero4()));
+                    if (lean) __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, add4(dxf_vz, dzf_vx), zero4()));
+                    else {
+                        __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxf_vz, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_vx, zero4()));
+                    }
                 }
             }
         }
@@ -494,7 +500,7 @@ elf_s(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) s_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        if (a.tflags[tile] == 1) s_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         else                s_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
@@ -528,6 +534,7 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
     const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
     const unsigned cm = col_mask<NN>(gx, g.nxp);
     const bool col_ok = gx < g.ld;
+    const bool lean = !PML && g.merge;     // merged history planes for damping-free tiles (see k1_tile / k2_tile)
     float4 DBX[RPT], DBZ[RPT], PXN[RPT], PXD[RPT], PZN[RPT], PZD[RPT], RPXD[RPT], RPZD[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
@@ -621,10 +628,15 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
                 st4(P + P_VXX * fp, q0); st4(P + P_VXZ * fp, q1); st4(P + P_VZX * fp, q2); st4(P + P_VZZ * fp, q3);
                 if (SAVE) {
                     float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + o;
-                    __stcs(reinterpret_cast<float4*>(H), sel4(m, dxf_txx, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_txz, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxb_txz, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_tzz, zero4()));
+                    if (lean) {          // damping-free tile: the adjoint only needs e1 + e2 and e3 + e4 (see k1_tile)
+                        __stcs(reinterpret_cast<float4*>(H), sel4(m, add4(dxf_txx, dzb_txz), zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, add4(dxb_txz, dzf_tzz), zero4()));
+                    } else {
+                        __stcs(reinterpret_cast<float4*>(H), sel4(m, dxf_txx, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_txz, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxb_txz, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_tzz, zero4()));
+                    }
                 }
             }
         }
@@ -673,7 +685,7 @@ elf_v(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) v_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
+        if (a.tflags[tile] == 1) v_tile<NN, true, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
         else                v_tile<NN, false, FS, SAVE>(&th, &tc, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
@@ -766,6 +778,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
     const int gx = X0 + R.c0, gz0 = Z0 + R.r0;
     const unsigned cm = col_mask<NN>(gx, g.nxp);
     const bool col_ok = gx < g.ld;
+    const bool lean = !PML && g.merge;     // merged history planes for damping-free tiles (see k1_tile / k2_tile)
     const size_t fp = (size_t)g.ns * g.plane;
     const int rbase = a.cur ? P_B0 : 0, wbase = a.cur ? 0 : P_B0;
     unsigned char* sst = smem + NSTAGE * G::F_VSTAGE;
@@ -851,8 +864,13 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                 for (int f = 0; f < 6; ++f) st4(P + f * fp, sp[f]);
                 if (SAVE) {
                     float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + o;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(H + (size_t)e * g.plane), sel4(m, d[e], zero4()));
+                    __stcs(reinterpret_cast<float4*>(H), sel4(m, d[0], zero4()));
+                    __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, d[1], zero4()));
+                    if (lean) __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, add4(d[2], d[3]), zero4()));
+                    else {
+                        __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, d[2], zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, d[3], zero4()));
+                    }
                 }
             }
         }
@@ -948,10 +966,15 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                 st4(P, q0); st4(P + fp, q1); st4(P + 2 * fp, q2); st4(P + 3 * fp, q3);
                 if (SAVE) {
                     float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + o;
-                    __stcs(reinterpret_cast<float4*>(H), sel4(m, dxf_txx, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_txz, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxb_txz, zero4()));
-                    __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_tzz, zero4()));
+                    if (lean) {          // damping-free tile: the adjoint only needs e1 + e2 and e3 + e4 (see k1_tile)
+                        __stcs(reinterpret_cast<float4*>(H), sel4(m, add4(dxf_txx, dzb_txz), zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, add4(dxb_txz, dzf_tzz), zero4()));
+                    } else {
+                        __stcs(reinterpret_cast<float4*>(H), sel4(m, dxf_txx, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + g.plane), sel4(m, dzb_txz, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 2 * g.plane), sel4(m, dxb_txz, zero4()));
+                        __stcs(reinterpret_cast<float4*>(H + 3 * g.plane), sel4(m, dzf_tzz, zero4()));
+                    }
                 }
             }
         }
@@ -1006,7 +1029,7 @@ elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) f_tile<NN, true, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        if (a.tflags[tile] == 1) f_tile<NN, true, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         else                f_tile<NN, false, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
@@ -1016,16 +1039,19 @@ elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
 // elf_k1 : adjoint of the velocity update
 // ==========================================================================================
 template <int NN> __device__ __forceinline__ void k1_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
-                                                           const CUtensorMap* th, int ns, int lcur, const CUtensorMap* thh, int hist_len, int tl)
+                                                           const CUtensorMap* th, int ns, int lcur, const CUtensorMap* thh, int hist_len, int tl,
+                                                           bool lean)
 {
+    // lean (damping-free tile, see elf_tile_class): the two splits of a pair hold the same bits, only the first one is
+    // staged; the history carries the merged derivatives in planes 4 and 6
 #pragma unroll
-    for (int e = 4; e < 8; ++e) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
+    for (int e = 4; e < 8; ++e) if (!lean || !(e & 1)) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
     using G = Geo<NN>;
     unsigned char* st = smem + k * G::K1_STAGE;
     fence_proxy_async();
-    mbar_expect_tx(bar + k, 6 * G::HF * 4);
+    mbar_expect_tx(bar + k, (lean ? 4 : 6) * G::HF * 4);
 #pragma unroll
-    for (int f = 0; f < 4; ++f) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LV + 4 * lcur + f) * ns + c.s, bar + k);
+    for (int f = 0; f < 4; ++f) if (!lean || !(f & 1)) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LV + 4 * lcur + f) * ns + c.s, bar + k);
     tma_load_3d(st + 4 * G::HB, th, c.X0 - HX, c.Z0 - NN, P_LVX * ns + c.s, bar + k);
     tma_load_3d(st + 5 * G::HB, th, c.X0 - HX, c.Z0 - NN, P_LVZ * ns + c.s, bar + k);
 }
@@ -1083,6 +1109,8 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap
         } else { PXD[j] = PZD[j] = PXN[j] = PZN[j] = RPXD[j] = RPZD[j] = one4(); }
         GBX[j] = zero4(); GBZ[j] = zero4();
     }
+    const bool lean = !PML && g.merge;                 // splits of a pair are bitwise equal on the whole staged rectangle
+    const bool deep = lean && a.tflags[tile] == 2;     // ... and no neighbouring tile reads the second split of this tile's cells
     const bool have_gv = a.nr > 0 && (a.g[3] || a.g[4]);
     const bool have_gs = a.nr > 0 && (a.g[0] || a.g[1] || a.g[2]);
     const bool inject_v = have_gv && a.rb.nbr[tile];
@@ -1092,7 +1120,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+            if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl, g.merge && a.tflags[pc.tile] != 1); pc.next(g, a.w, ring); }
     }
 
     for (int s = s_lo; s < s_hi; ++s) {
@@ -1107,7 +1135,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap
             const float* H = a.hist + (((size_t)s * a.hist_len + a.tl) * NHIST + 4) * g.plane + (size_t)gz * g.ld + gx;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                E[e][j] = (col_ok && gz < g.nzp) ? __ldcs(reinterpret_cast<const float4*>(H + (size_t)e * g.plane)) : zero4();
+                E[e][j] = (col_ok && gz < g.nzp && !(lean && (e & 1))) ? __ldcs(reinterpret_cast<const float4*>(H + (size_t)e * g.plane)) : zero4();
         }
         ELF_WAIT_STAGE(k);
         if (inject_v) {          // 10T: cotangents of the vx / vz records into the staged sums (duplicates legal)
@@ -1153,16 +1181,23 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap
             const int r = R.r0 + j, gz = gz0 + j;
             const int hb = (r + NN) * RXH + R.c0 + HX;
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
-            const float4 L0 = ld4(L + hb), L1 = ld4(L + G::HB / 4 + hb), L2 = ld4(L + 2 * (G::HB / 4) + hb), L3 = ld4(L + 3 * (G::HB / 4) + hb);
+            const float4 L0 = ld4(L + hb), L2 = ld4(L + 2 * (G::HB / 4) + hb);
+            const float4 L1 = lean ? L0 : ld4(L + G::HB / 4 + hb), L3 = lean ? L2 : ld4(L + 3 * (G::HB / 4) + hb);
             float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
             k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + hb), ld4(lvz + hb), BX[j], BZ[j], PXN[j], PXD[j], PZN[j], PZD[j], RPXD[j], RPZD[j],
                          w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
             st4(L + hb, m1); st4(L + G::HB / 4 + hb, m2); st4(L + 2 * (G::HB / 4) + hb, m3); st4(L + 3 * (G::HB / 4) + hb, m4);
-            GBX[j] = add4(GBX[j], add4(mul4(w1, E[0][j]), mul4(w2, E[1][j])));
-            GBZ[j] = add4(GBZ[j], add4(mul4(w3, E[2][j]), mul4(w4, E[3][j])));
+            if (lean) {          // w1 == w2, w3 == w4 (dx == dz): the history holds e1 + e2 and e3 + e4
+                GBX[j] = add4(GBX[j], mul4(w1, E[0][j]));
+                GBZ[j] = add4(GBZ[j], mul4(w3, E[2][j]));
+            } else {
+                GBX[j] = add4(GBX[j], add4(mul4(w1, E[0][j]), mul4(w2, E[1][j])));
+                GBZ[j] = add4(GBZ[j], add4(mul4(w3, E[2][j]), mul4(w4, E[3][j])));
+            }
             if (col_ok && gz < g.nzp) {
                 float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LV + 4 * (a.lcur ^ 1)) * fp;
-                st4(P, N0); st4(P + fp, N1); st4(P + 2 * fp, N2); st4(P + 3 * fp, N3);
+                st4(P, N0); st4(P + 2 * fp, N2);
+                if (!deep) { st4(P + fp, N1); st4(P + 3 * fp, N3); }
             }
         }
         for (int i = tid; i < G::NRING; i += NTH) {     // ring: m only (coefficients from the L2-resident pack)
@@ -1179,7 +1214,8 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap
                 pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
                 rpxd = div4(one4(), pxd); rpzd = div4(one4(), pzd);
             }
-            const float4 L0 = ld4(L + hb), L1 = ld4(L + G::HB / 4 + hb), L2 = ld4(L + 2 * (G::HB / 4) + hb), L3 = ld4(L + 3 * (G::HB / 4) + hb);
+            const float4 L0 = ld4(L + hb), L2 = ld4(L + 2 * (G::HB / 4) + hb);
+            const float4 L1 = lean ? L0 : ld4(L + G::HB / 4 + hb), L3 = lean ? L2 : ld4(L + 3 * (G::HB / 4) + hb);
             float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
             k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + hb), ld4(lvz + hb), ldk4(a.cp.bx + o, pol), ldk4(a.cp.bz + o, pol), pxn, pxd, pzn, pzd, rpxd, rpzd,
                          w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
@@ -1223,7 +1259,7 @@ __device__ __forceinline__ void k1_tile(const CUtensorMap* th, const CUtensorMap
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+        if (tid == 0 && pc.valid) { k1_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl, g.merge && a.tflags[pc.tile] != 1); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -1261,7 +1297,7 @@ elf_k1(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorM
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) k1_tile<NN, true, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
+        if (a.tflags[tile] == 1) k1_tile<NN, true, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
         else                k1_tile<NN, false, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, R, tid, tile, chunk, s_lo, s_hi, first);
         __syncthreads();
     }
@@ -1271,18 +1307,20 @@ elf_k1(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorM
 // elf_k2 : adjoint of the stress update (Appendix A.2, steps 5T..1T)
 // ==========================================================================================
 template <int NN> __device__ __forceinline__ void k2_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
-                                                           const CUtensorMap* th, int ns, int lcur, const CUtensorMap* thh, int hist_len, int tl)
+                                                           const CUtensorMap* th, int ns, int lcur, const CUtensorMap* thh, int hist_len, int tl,
+                                                           bool lean)
 {
+    // lean: see k1_issue; the history carries D-x vx, D-z vz and the merged D+x vz + D+z vx in planes 0..2
 #pragma unroll
-    for (int e = 0; e < 4; ++e) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
+    for (int e = 0; e < 4; ++e) if (!lean || e < 3) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
     using G = Geo<NN>;
     unsigned char* st = smem + k * G::K2_STAGE;
     fence_proxy_async();
-    mbar_expect_tx(bar + k, 9 * G::HF * 4);
+    mbar_expect_tx(bar + k, (lean ? 6 : 9) * G::HF * 4);
 #pragma unroll
     for (int f = 0; f < 3; ++f) tma_load_3d(st + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_MXX + f) * ns + c.s, bar + k);
 #pragma unroll
-    for (int f = 0; f < 6; ++f) tma_load_3d(st + (3 + f) * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LS + 6 * lcur + f) * ns + c.s, bar + k);
+    for (int f = 0; f < 6; ++f) if (!lean || !(f & 1)) tma_load_3d(st + (3 + f) * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LS + 6 * lcur + f) * ns + c.s, bar + k);
 }
 
 template <bool PML>
@@ -1326,6 +1364,8 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap
     const unsigned cm = col_mask<NN>(gx, g.nxp);
     const bool col_ok = gx < g.ld;
     const size_t fp = (size_t)g.ns * g.plane;
+    const bool lean = !PML && g.merge;                 // see k1_tile
+    const bool deep = lean && a.tflags[tile] == 2;
     if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
     float4 C11[RPT], C13[RPT], C33[RPT], C55[RPT], PXN[RPT], PXI[RPT], PZN[RPT], PZI[RPT], G11[RPT], G13[RPT], G33[RPT], G55[RPT];
 #pragma unroll
@@ -1345,7 +1385,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+            if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl, g.merge && a.tflags[pc.tile] != 1); pc.next(g, a.w, ring); }
     }
     __syncthreads();
 
@@ -1362,7 +1402,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap
             const float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + (size_t)gz * g.ld + gx;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                D[e][j] = (col_ok && gz < g.nzp) ? __ldcs(reinterpret_cast<const float4*>(H + (size_t)e * g.plane)) : zero4();
+                D[e][j] = (col_ok && gz < g.nzp && !(lean && e == 3)) ? __ldcs(reinterpret_cast<const float4*>(H + (size_t)e * g.plane)) : zero4();
         }
         ELF_WAIT_STAGE(k);
         if (FS && tzi == 0) {    // 5T: transpose of the free-surface stress mirrors
@@ -1387,18 +1427,19 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
             float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) LS[f] = ld4(LSr + f * HQ + hb);
+            for (int f = 0; f < 6; f += 2) { LS[f] = ld4(LSr + f * HQ + hb); LS[f + 1] = lean ? LS[f] : ld4(LSr + (f + 1) * HQ + hb); }
             k2_cell<PML>(g, m, LS, ld4(MS + hb), ld4(mzz_r + hb), ld4(mxz_r + hb), C11[j], C13[j], C33[j], C55[j], PXN[j], PXI[j], PZN[j], PZI[j],
                          l, q, nA, nB, nC, nD, N);
             st4(LSr + hb, nA); st4(LSr + HQ + hb, nB); st4(LSr + 4 * HQ + hb, nC); st4(LSr + 5 * HQ + hb, nD);
             G11[j] = add4(G11[j], mul4(q[0], D[0][j]));
             G13[j] = add4(G13[j], add4(mul4(q[1], D[1][j]), mul4(q[2], D[0][j])));
             G33[j] = add4(G33[j], mul4(q[3], D[1][j]));
-            G55[j] = add4(G55[j], add4(mul4(q[4], D[2][j]), mul4(q[5], D[3][j])));
+            if (lean) G55[j] = add4(G55[j], mul4(q[4], D[2][j]));       // q4 == q5 (dt/dx == dt/dz): the history holds d3 + d4
+            else      G55[j] = add4(G55[j], add4(mul4(q[4], D[2][j]), mul4(q[5], D[3][j])));
             if (col_ok && gz < g.nzp) {
                 float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LS + 6 * (a.lcur ^ 1)) * fp;
 #pragma unroll
-                for (int f = 0; f < 6; ++f) st4(P + f * fp, N[f]);
+                for (int f = 0; f < 6; ++f) if (!deep || !(f & 1)) st4(P + f * fp, N[f]);
                 if (a.g_src && m != 0u && s_sz[s - s_lo] == gz) {       // 3T
                     const int dc = s_sx[s - s_lo] - gx;
                     if (dc >= 0 && dc < 4 && ((m >> dc) & 1u)) {
@@ -1426,7 +1467,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap
             }
             float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
 #pragma unroll
-            for (int f = 0; f < 6; ++f) LS[f] = ld4(LSr + f * HQ + hb);
+            for (int f = 0; f < 6; f += 2) { LS[f] = ld4(LSr + f * HQ + hb); LS[f + 1] = lean ? LS[f] : ld4(LSr + (f + 1) * HQ + hb); }
             k2_cell<PML>(g, m, LS, ld4(MS + hb), ld4(mzz_r + hb), ld4(mxz_r + hb), ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol),
                          ldk4(a.cp.c33 + o, pol), ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, l, q, nA, nB, nC, nD, N);
             st4(LSr + hb, nA); st4(LSr + HQ + hb, nB); st4(LSr + 4 * HQ + hb, nC); st4(LSr + 5 * HQ + hb, nD);
@@ -1457,7 +1498,7 @@ __device__ __forceinline__ void k2_tile(const CUtensorMap* th, const CUtensorMap
         }
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+        if (tid == 0 && pc.valid) { k2_issue<NN>(pc, smem, bar, k, th, g.ns, a.lcur, thh, a.hist_len, a.tl, g.merge && a.tflags[pc.tile] != 1); pc.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -1497,7 +1538,7 @@ elf_k2(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorM
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile]) k2_tile<NN, true, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        if (a.tflags[tile] == 1) k2_tile<NN, true, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
         else                k2_tile<NN, false, FS>(&th, &thh, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
         __syncthreads();
     }
@@ -1532,6 +1573,29 @@ __global__ void elf_tile_flags(int ntx, int cpld, size_t cpplane, const float* _
     }
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) flags[tile] = (unsigned char)(bad ? 1 : 0);
+}
+// tile classes for the lean adjoint (EGeom::merge): on a damping-free cell both halves of every split pair go through
+// identical arithmetic from identical (zero) initial values -- pmln = pmld = 1 exactly -- so their cotangents are bitwise
+// equal for all time.  A tile of class 0 or 2 (no damping on tile + apron) stages only the first half of each pair.
+//   1 = PML tile: full split treatment;
+//   0 = damping-free tile next to a PML tile: reads first halves, writes both (the PML tile's halo reads them);
+//   2 = damping-free tile whose 8 neighbours are damping-free too: reads and writes first halves only.
+// In place on the 0/1 flags: a concurrent reader only tests "== 1".
+__global__ void elf_tile_class(int ntx, int ntz, unsigned char* __restrict__ flags)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntx * ntz) return;
+    const volatile unsigned char* f = flags;
+    if (f[t] == 1) return;
+    const int tz = t / ntx, tx = t - tz * ntx;
+    int pml = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int z2 = tz + dz, x2 = tx + dx;
+            if (z2 < 0 || z2 >= ntz || x2 < 0 || x2 >= ntx) continue;
+            pml |= (f[z2 * ntx + x2] == 1);
+        }
+    flags[t] = (unsigned char)(pml ? 0 : 2);
 }
 // receiver buckets: counting sort of the receivers by tile
 __device__ __forceinline__ int rcv_tile(int nzp, int nxp, int ntx, int64_t z, int64_t x)
@@ -1626,6 +1690,15 @@ int elf_num_sms()
     return n;
 }
 
+// lean adjoint on damping-free tiles (needs dx == dz, which the reference asserts: ADFWI/model/base.py:79);
+// ADFWI_B200_EL_LEAN=0 keeps the full split treatment everywhere (A/B switch for tests and profiles)
+inline bool elf_lean_adjoint()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_EL_LEAN"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 struct EFPlan {
     EGeom g;
     int ns, nr, NN, FS, save, n_segments, nz, nx, nabc, zoff;
@@ -1650,6 +1723,7 @@ int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
     g.plane = (size_t)g.nzp * g.ld;
     g.dt = d->dt; g.dx = d->dx; g.dz = d->dz; g.dt_dx = d->dt_dx; g.dt_dz = d->dt_dz; g.half_dt = d->half_dt;
     g.rdx = 1.0f / d->dx; g.rdz = 1.0f / d->dz;
+    g.merge = (g.rdx == g.rdz && g.dt_dx == g.dt_dz && elf_lean_adjoint()) ? 1 : 0;
     for (int k = 0; k < 3; ++k) g.c[k] = d->fdc[k];
     P->cprows = g.ntz * TZ + 2 * CPZ;
     P->cpplane = align_up((size_t)P->cprows * g.cpld, 64);
@@ -1712,6 +1786,10 @@ int elf_setup(const EFPlan& P, cudaStream_t st, const float* const* coef, const 
     const int ntiles = g.ntx * g.ntz;
     elf_tile_flags<<<ntiles, 128, 0, st>>>(g.ntx, g.cpld, P.cpplane, P.pack, P.tflags);
     ADFWI_LAUNCH_CHECK();
+    if (g.merge) {
+        elf_tile_class<<<cdiv(ntiles, 128), 128, 0, st>>>(g.ntx, g.ntz, P.tflags);
+        ADFWI_LAUNCH_CHECK();
+    }
     ADFWI_CUDA(cudaMemsetAsync(P.rcv_cnt, 0, sizeof(int) * (ntiles + 1), st));
     if (P.nr > 0) {
         elf_rcv_count<<<cdiv(P.nr, 128), 128, 0, st>>>(g.nzp, g.nxp, g.ntx, P.nr, rx, rz, P.rcv_cnt);
