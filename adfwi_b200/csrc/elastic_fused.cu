@@ -76,6 +76,7 @@ enum { P_VXX = 0, P_VXZ, P_VZX, P_VZZ, P_S0, P_S1, P_S2, P_S3, P_S4, P_S5, P_TXX
        P_LS = P_LV + 8,             // 2 x 6 stress-split cotangents (ping-pong)
        P_LVX = P_LS + 12, P_LVZ,    // cotangents of the velocity sums
        P_MXX, P_MZZ, P_MXZ,         // cotangents of the stress sums (between elf_k1 and elf_k2)
+       P_LVX2, P_LVZ2,              // second set of the velocity-sum cotangents (ping-pong of the fused reverse kernel elf_b)
        P_COUNT };
 constexpr int NHIST = 8;            // history planes per step: dxb_vx, dzb_vz, dxf_vz, dzf_vx, dxf_txx, dzb_txz, dxb_txz, dzf_tzz
 
@@ -1544,6 +1545,393 @@ elf_k2(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorM
     }
 }
 
+// ==========================================================================================
+// elf_b : fused reverse step = elf_k1 + elf_k2 in one launch (O(2,4); Appendix A.2, steps 10T..1T)
+//
+// The adjoint of the velocity update is evaluated on the tile plus a ring of 2NN cells (own-cell transposes) and
+// NN cells (operator-transpose gathers), so the adjoint of the stress update finds the cotangents of the stress
+// sums in shared memory: they never travel to HBM, and the cotangents of the velocity sums make one round trip
+// per step instead of two.  Per shot two TMA groups arrive in SINGLE buffers that are refilled as soon as their
+// consumer phase is over, so each load has half a shot of compute to hide behind:
+//   V : 4 velocity-split cotangents + cotangents of the two velocity sums, halo 2NN  (free after the first gather)
+//   S : 6 stress-split cotangents, halo NN                                          (free after the second gather)
+// plus a scratch group M (3 rects: cotangents of the stress sums on tile + ring).  All split cotangents and the two
+// sum cotangents are written to the other set of a ping-pong pair (neighbouring tiles still read the old ring).
+// HBM traffic per cell-update, damping-free tiles: 4 + 3 staged planes read, 5 history planes, 2 + 3 + 2 written.
+// ==========================================================================================
+struct BArgs { ECoef cp; const unsigned char* tflags; float* planes; const float* hist; int hist_len, tl, it, lcur;
+               int nr; RcvB rb; const float* g[5]; const float* mt; const int64_t *sx, *sz; float* g_src; float* gpart; Walk w; };
+
+template <int NN> struct GeoB {
+    using G = Geo<NN>;
+    static constexpr int GX2 = G::HX2 / 4;                    // halo float4 groups on each side of a V rect
+    static constexpr int W2 = NG + 2 * GX2;
+    static constexpr int NRING2 = 4 * NN * W2 + TZ * 2 * GX2; // float4 groups of the 2NN ring
+    static constexpr int V_BYTES = 6 * G::HB2, S_BYTES = 6 * G::HB, M_BYTES = 3 * G::HB;
+    static constexpr int SMEM = V_BYTES + S_BYTES + M_BYTES;
+};
+// ring float4 group i in [0, NRING2): rows [-2NN,0) and [TZ,TZ+2NN) x groups [-GX2, NG+GX2), rows [0,TZ) x the side groups
+template <int NN> __device__ __forceinline__ void ring2_cell(int i, int& r, int& gi)
+{
+    constexpr int GX2 = GeoB<NN>::GX2, W = GeoB<NN>::W2;
+    if (i < 2 * NN * W) { r = -2 * NN + i / W; gi = i % W - GX2; }
+    else if (i < 4 * NN * W) { const int ii = i - 2 * NN * W; r = TZ + ii / W; gi = ii % W - GX2; }
+    else { const int ii = i - 4 * NN * W; r = ii / (2 * GX2); const int k = ii - r * (2 * GX2); gi = k < GX2 ? k - GX2 : NG + (k - GX2); }
+}
+// segment load at the edge of a staged rectangle: a missing neighbour group reads as zero (its values only reach
+// ring cells that no consumer uses)
+__device__ __forceinline__ void ldseg_e(const float* p, float* s, bool hl, bool hr)
+{
+    const float4 a = hl ? ld4(p - 4) : zero4(), b = ld4(p), c = hr ? ld4(p + 4) : zero4();
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w; s[8] = c.x; s[9] = c.y; s[10] = c.z; s[11] = c.w;
+}
+
+template <int NN> __device__ __forceinline__ void b_issue_v(const Cursor& c, unsigned char* smem, uint64_t* bar, const CUtensorMap* th2,
+                                                            const CUtensorMap* thh, int ns, int lcur, int hist_len, int tl, bool lean)
+{
+    using G = Geo<NN>;
+    // history planes of the shot into L2 (read with plain loads by the consumers): 0..3 for the stress part (lean: the
+    // merged plane 2 replaces 2 and 3), 4..7 for the velocity part (lean: merged planes 4 and 6)
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (!lean || (e < 3) || e == 4 || e == 6) tma_prefetch_3d(thh, c.X0, c.Z0, (c.s * hist_len + tl) * NHIST + e);
+    fence_proxy_async();
+    mbar_expect_tx(bar, (lean ? 4 : 6) * G::HF2 * 4);
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+        if (!lean || !(f & 1)) tma_load_3d(smem + f * G::HB2, th2, c.X0 - G::HX2, c.Z0 - 2 * NN, (P_LV + 4 * lcur + f) * ns + c.s, bar);
+    tma_load_3d(smem + 4 * G::HB2, th2, c.X0 - G::HX2, c.Z0 - 2 * NN, (lcur ? P_LVX2 : P_LVX) * ns + c.s, bar);
+    tma_load_3d(smem + 5 * G::HB2, th2, c.X0 - G::HX2, c.Z0 - 2 * NN, (lcur ? P_LVZ2 : P_LVZ) * ns + c.s, bar);
+}
+template <int NN> __device__ __forceinline__ void b_issue_s(const Cursor& c, unsigned char* sst, uint64_t* bar, const CUtensorMap* th,
+                                                            int ns, int lcur, bool lean)
+{
+    using G = Geo<NN>;
+    fence_proxy_async();
+    mbar_expect_tx(bar, (lean ? 3 : 6) * G::HF * 4);
+#pragma unroll
+    for (int f = 0; f < 6; ++f)
+        if (!lean || !(f & 1)) tma_load_3d(sst + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (P_LS + 6 * lcur + f) * ns + c.s, bar);
+}
+
+template <int NN, bool PML, bool FS>
+__device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap* th2, const CUtensorMap* thh, const EGeom& g, const BArgs& a,
+                                       unsigned char* smem, uint64_t* bar, uint32_t& par, Cursor& pcv, Cursor& pcs, int* ring,
+                                       int* s_sz, int* s_sx, const Roles& R, int tid, int tile, int chunk, int s_lo, int s_hi, bool first)
+{
+    using G = Geo<NN>;
+    using B = GeoB<NN>;
+    constexpr int RX2 = G::RX2, HX2 = G::HX2, HQ = G::HB / 4, HQ2 = G::HB2 / 4, GX2 = B::GX2;
+    const uint64_t pol = l2_keep_policy();
+    const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
+    const int X0 = txi * TX, Z0 = tzi * TZ;
+    const int gx = X0 + R.c0, gz = Z0 + R.r0;
+    const unsigned cm = col_mask<NN>(gx, g.nxp);
+    const unsigned mt_ = row_in<NN>(gz, g.nzp) ? cm : 0u;          // update-region mask of the thread's own group
+    const bool cell_ok = gx < g.ld && gz < g.nzp;
+    const size_t fp = (size_t)g.ns * g.plane;
+    const bool lean = !PML && g.merge;                 // see k1_tile
+    const bool deep = lean && a.tflags[tile] == 2;
+    float* V = (float*)smem;                            // rects 0..3: velocity-split cotangents (become m1..m4), 4: lvx, 5: lvz
+    float* lvx = V + 4 * HQ2; float* lvz = V + 5 * HQ2;
+    unsigned char* sst = smem + B::V_BYTES;
+    float* LSr = (float*)sst;                           // 6 stress-split cotangents; rects 0, 1, 4, 5 become nA, nB, nC, nD
+    float* mxx_r = (float*)(sst + B::S_BYTES); float* mzz_r = mxx_r + HQ; float* mxz_r = mxx_r + 2 * HQ;
+    const int hv = (R.r0 + 2 * NN) * RX2 + R.c0 + HX2, hs = (R.r0 + NN) * RXH + R.c0 + HX;
+    if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
+    const ptrdiff_t oc = (ptrdiff_t)gz * g.cpld + gx;
+    const float4 C11 = ldk4(a.cp.c11 + oc, pol), C13 = ldk4(a.cp.c13 + oc, pol), C33 = ldk4(a.cp.c33 + oc, pol), C55 = ldk4(a.cp.c55 + oc, pol);
+    const float4 BX = ldk4(a.cp.bx + oc, pol), BZ = ldk4(a.cp.bz + oc, pol);
+    float4 PXN = one4(), PZN = one4(), PXI = one4(), PZI = one4();
+    if (PML) {
+        const float4 bx_ = ldk4(a.cp.bcx + oc, pol), bz_ = ldk4(a.cp.bcz + oc, pol);
+        PXN = sub4(one4(), smul(g.half_dt, bx_)); PZN = sub4(one4(), smul(g.half_dt, bz_));
+        PXI = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); PZI = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+    }
+    float4 G11 = zero4(), G13 = zero4(), G33 = zero4(), G55 = zero4(), GBX = zero4(), GBZ = zero4();
+    const bool have_gv = a.nr > 0 && (a.g[3] || a.g[4]);
+    const bool have_gs = a.nr > 0 && (a.g[0] || a.g[1] || a.g[2]);
+    const bool inject_v = have_gv && a.rb.nbr[tile];
+    const bool inject_s = have_gs && a.rb.nbr[tile];
+    if (first) {
+        griddep_wait();
+        if (tid == 0) {
+            if (pcv.valid) { b_issue_v<NN>(pcv, smem, bar, th2, thh, g.ns, a.lcur, a.hist_len, a.tl, g.merge && a.tflags[pcv.tile] != 1); pcv.next(g, a.w, ring); }
+            if (pcs.valid) { b_issue_s<NN>(pcs, sst, bar + 1, th, g.ns, a.lcur, g.merge && a.tflags[pcs.tile] != 1); pcs.next_follow(g, a.w, ring); }
+        }
+    }
+    __syncthreads();
+
+    for (int s = s_lo; s < s_hi; ++s) {
+        const float* H = a.hist + ((size_t)s * a.hist_len + a.tl) * NHIST * g.plane + (size_t)gz * g.ld + gx;
+        // history of the velocity update (own cell): e1 = D+x txx, e2 = D-z txz, e3 = D-x txz, e4 = D+z tzz (lean: e1+e2, e3+e4)
+        float4 E0 = zero4(), E1 = zero4(), E2 = zero4(), E3 = zero4();
+        if (cell_ok) {
+            E0 = __ldcs(reinterpret_cast<const float4*>(H + 4 * g.plane)); E2 = __ldcs(reinterpret_cast<const float4*>(H + 6 * g.plane));
+            if (!lean) { E1 = __ldcs(reinterpret_cast<const float4*>(H + 5 * g.plane)); E3 = __ldcs(reinterpret_cast<const float4*>(H + 7 * g.plane)); }
+        }
+        ELF_WAIT_STAGE(0);
+        if (inject_v) {          // 10T: cotangents of the vx / vz records into the staged sums (duplicates legal)
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int tz2 = tzi + dz;
+                if (tz2 < 0 || tz2 >= g.ntz) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int tx2 = txi + dx;
+                    if (tx2 < 0 || tx2 >= g.ntx) continue;
+                    const int t2 = tz2 * g.ntx + tx2;
+                    const int lo = a.rb.start[t2], hi = a.rb.start[t2 + 1];
+                    for (int i = lo + tid; i < hi; i += NTH) {
+                        const int zx = a.rb.zx[i];
+                        const int z = (zx >> 16) - (Z0 - 2 * NN), x = (zx & 0xffff) - (X0 - HX2);
+                        if (z >= 0 && z < G::RZ2 && x >= 0 && x < RX2) {
+                            const size_t o = ((size_t)s * g.nt + a.it) * a.nr + a.rb.id[i];
+                            if (a.g[3]) atomicAdd(lvx + z * RX2 + x, a.g[3][o]);
+                            if (a.g[4]) atomicAdd(lvz + z * RX2 + x, a.g[4][o]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (FS && tzi == 0) {    // 9T: transpose of the free-surface velocity edits (adds into rows h-1, h)
+            const int t = tid;
+            if (t >= 1 && t < RX2) {
+                const int j = X0 + t - HX2;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (3 * NN) * RX2 + t, rh = (3 * NN + 1) * RX2 + t, rh2 = (3 * NN - 1) * RX2 + t, rh3 = (3 * NN - 2) * RX2 + t;
+                    const float qj = lvx[rh2];
+                    const float qm = (j - 1 >= NN) ? lvx[rh2 - 1] : 0.f;
+                    const float add_vz = lvz[rh2] + lvz[rh3] + 2.0f * (qm - qj);
+                    lvz[rh1] += add_vz;
+                    lvx[rh] += qj;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase A: own-cell transpose of the velocity update on tile + 2NN ring; m1..m4 replace the split cotangents ----
+        {
+            const float4 L0 = ld4(V + hv), L2 = ld4(V + 2 * HQ2 + hv);
+            const float4 L1 = lean ? L0 : ld4(V + HQ2 + hv), L3 = lean ? L2 : ld4(V + 3 * HQ2 + hv);
+            float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
+            k1_cell<PML>(g, mt_, L0, L1, L2, L3, ld4(lvx + hv), ld4(lvz + hv), BX, BZ, PXN, PXN, PZN, PZN, PXI, PZI,
+                         w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
+            st4(V + hv, m1); st4(V + HQ2 + hv, m2); st4(V + 2 * HQ2 + hv, m3); st4(V + 3 * HQ2 + hv, m4);
+            if (lean) {          // w1 == w2, w3 == w4 (dx == dz): the history holds e1 + e2 and e3 + e4
+                GBX = add4(GBX, mul4(w1, E0));
+                GBZ = add4(GBZ, mul4(w3, E2));
+            } else {
+                GBX = add4(GBX, add4(mul4(w1, E0), mul4(w2, E1)));
+                GBZ = add4(GBZ, add4(mul4(w3, E2), mul4(w4, E3)));
+            }
+            if (cell_ok) {
+                float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LV + 4 * (a.lcur ^ 1)) * fp;
+                st4(P, N0); st4(P + 2 * fp, N2);
+                if (!deep) { st4(P + fp, N1); st4(P + 3 * fp, N3); }
+            }
+        }
+        for (int i = tid; i < B::NRING2; i += NTH) {
+            int r, gi;
+            ring2_cell<NN>(i, r, gi);
+            const int gzr = Z0 + r, gxr = X0 + 4 * gi;
+            const int h2 = (r + 2 * NN) * RX2 + 4 * gi + HX2;
+            const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
+            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
+            float4 pxn = one4(), pzn = one4(), rpxd = one4(), rpzd = one4();
+            if (PML) {
+                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
+                rpxd = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); rpzd = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+            }
+            const float4 L0 = ld4(V + h2), L2 = ld4(V + 2 * HQ2 + h2);
+            const float4 L1 = lean ? L0 : ld4(V + HQ2 + h2), L3 = lean ? L2 : ld4(V + 3 * HQ2 + h2);
+            float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
+            k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + h2), ld4(lvz + h2), ldk4(a.cp.bx + o, pol), ldk4(a.cp.bz + o, pol), pxn, pxn, pzn, pzn, rpxd, rpzd,
+                         w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
+            st4(V + h2, m1); st4(V + HQ2 + h2, m2); st4(V + 2 * HQ2 + h2, m3); st4(V + 3 * HQ2 + h2, m4);
+        }
+        __syncthreads();
+        // history of the stress update (own cell): D-x vx, D-z vz, D+x vz, D+z vx (lean: the last two merged); in flight during phase B
+        float4 D0 = zero4(), D1 = zero4(), D2 = zero4(), D3 = zero4();
+        if (cell_ok) {
+            D0 = __ldcs(reinterpret_cast<const float4*>(H)); D1 = __ldcs(reinterpret_cast<const float4*>(H + g.plane));
+            D2 = __ldcs(reinterpret_cast<const float4*>(H + 2 * g.plane));
+            if (!lean) D3 = __ldcs(reinterpret_cast<const float4*>(H + 3 * g.plane));
+        }
+        // ---- phase B: 6T gathers -> cotangents of the stress sums on tile + NN ring (shared memory only) ----
+        {
+            const float* M1 = V; const float* M2 = V + HQ2; const float* M3 = V + 2 * HQ2; const float* M4 = V + 3 * HQ2;
+            for (int i = tid; i < NTH + G::NRING; i += NTH) {
+                int r = R.r0, gi = R.l;
+                if (i >= NTH) ring_cell<NN>(i - NTH, r, gi);
+                const int h2 = (r + 2 * NN) * RX2 + 4 * gi + HX2, h1 = (r + NN) * RXH + 4 * gi + HX;
+                float s1[12], s3[12];
+                ldseg_e(M1 + h2, s1, gi - 1 >= -GX2, gi + 1 < NG + GX2); ldseg_e(M3 + h2, s3, gi - 1 >= -GX2, gi + 1 < NG + GX2);
+                float4 w2[2 * NN], w4[2 * NN];
+#pragma unroll
+                for (int q = 0; q < 2 * NN; ++q) {
+                    w2[q] = ld4(M2 + h2 + (q - NN + 1) * RX2);      // (D-z)^T: rows i-NN+1 .. i+NN
+                    w4[q] = ld4(M4 + h2 + (q - NN) * RX2);          // (D+z)^T: rows i-NN .. i+NN-1
+                }
+                st4(mxx_r + h1, xgath<NN, 0>(s1, g.c));
+                st4(mxz_r + h1, add4(zgath<NN>(w2, g.c), xgath<NN, 1>(s3, g.c)));
+                st4(mzz_r + h1, zgath<NN>(w4, g.c));
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // group V has been consumed: refill it with the next shot while the stress part runs
+        if (tid == 0 && pcv.valid) { b_issue_v<NN>(pcv, smem, bar, th2, thh, g.ns, a.lcur, a.hist_len, a.tl, g.merge && a.tflags[pcv.tile] != 1); pcv.next(g, a.w, ring); }
+        if (inject_s) {          // 10T: cotangents of the stress records add to the sums' cotangents (tile + ring)
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int tz2 = tzi + dz;
+                if (tz2 < 0 || tz2 >= g.ntz) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int tx2 = txi + dx;
+                    if (tx2 < 0 || tx2 >= g.ntx) continue;
+                    const int t2 = tz2 * g.ntx + tx2;
+                    const int lo = a.rb.start[t2], hi = a.rb.start[t2 + 1];
+                    for (int i = lo + tid; i < hi; i += NTH) {
+                        const int zx = a.rb.zx[i];
+                        const int z = (zx >> 16) - (Z0 - NN), x = (zx & 0xffff) - (X0 - HX);
+                        if (z >= 0 && z < G::RZH && x >= 0 && x < RXH) {
+                            const size_t o = ((size_t)s * g.nt + a.it) * a.nr + a.rb.id[i];
+                            if (a.g[0]) atomicAdd(mxx_r + z * RXH + x, a.g[0][o]);
+                            if (a.g[1]) atomicAdd(mzz_r + z * RXH + x, a.g[1][o]);
+                            if (a.g[2]) atomicAdd(mxz_r + z * RXH + x, a.g[2][o]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (FS && tzi == 0) {    // 5T: transpose of the free-surface stress mirrors
+            const int t = tid;
+            if (t < RXH) {
+                const int j = X0 + t - HX;
+                if (j >= NN && j < g.nxp - NN) {
+                    const int rh1 = (2 * NN) * RXH + t, rh = (2 * NN + 1) * RXH + t, rh2 = (2 * NN - 1) * RXH + t, rh3 = (2 * NN - 2) * RXH + t;
+                    mxz_r[rh] -= mxz_r[rh3];
+                    mzz_r[rh] -= mzz_r[rh2];
+                    mxz_r[rh1] -= mxz_r[rh2];
+                    mzz_r[rh1] = 0.f;
+                }
+            }
+            __syncthreads();
+        }
+        ELF_WAIT_STAGE(1);
+        // ---- phase C: own-cell transpose of the stress update on tile + NN ring; nA..nD replace four split cotangents ----
+        {
+            float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
+#pragma unroll
+            for (int f = 0; f < 6; f += 2) { LS[f] = ld4(LSr + f * HQ + hs); LS[f + 1] = lean ? LS[f] : ld4(LSr + (f + 1) * HQ + hs); }
+            k2_cell<PML>(g, mt_, LS, ld4(mxx_r + hs), ld4(mzz_r + hs), ld4(mxz_r + hs), C11, C13, C33, C55, PXN, PXI, PZN, PZI, l, q, nA, nB, nC, nD, N);
+            st4(LSr + hs, nA); st4(LSr + HQ + hs, nB); st4(LSr + 4 * HQ + hs, nC); st4(LSr + 5 * HQ + hs, nD);
+            G11 = add4(G11, mul4(q[0], D0));
+            G13 = add4(G13, add4(mul4(q[1], D1), mul4(q[2], D0)));
+            G33 = add4(G33, mul4(q[3], D1));
+            if (lean) G55 = add4(G55, mul4(q[4], D2));       // q4 == q5 (dt/dx == dt/dz): the history holds d3 + d4
+            else      G55 = add4(G55, add4(mul4(q[4], D2), mul4(q[5], D3)));
+            if (cell_ok) {
+                float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LS + 6 * (a.lcur ^ 1)) * fp;
+#pragma unroll
+                for (int f = 0; f < 6; ++f) if (!deep || !(f & 1)) st4(P + f * fp, N[f]);
+                if (a.g_src && mt_ != 0u && s_sz[s - s_lo] == gz) {       // 3T
+                    const int dc = s_sx[s - s_lo] - gx;
+                    if (dc >= 0 && dc < 4 && ((mt_ >> dc) & 1u)) {
+                        const float* Mt = a.mt + (size_t)s * 9;
+                        a.g_src[(size_t)s * g.nt + a.it] = -(Mt[0] / 2.0f) * (comp4(l[0], dc) + comp4(l[1], dc))
+                                                          - (Mt[8] / 2.0f) * (comp4(l[2], dc) + comp4(l[3], dc))
+                                                          - (Mt[2] / 2.0f) * (comp4(l[4], dc) + comp4(l[5], dc));
+                    }
+                }
+            }
+        }
+        for (int i = tid; i < G::NRING; i += NTH) {
+            int r, gi;
+            ring_cell<NN>(i, r, gi);
+            const int gzr = Z0 + r, gxr = X0 + 4 * gi;
+            const int h1 = (r + NN) * RXH + 4 * gi + HX;
+            const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
+            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
+            float4 pxn = one4(), pxi = one4(), pzn = one4(), pzi = one4();
+            if (PML) {
+                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
+                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
+                pxi = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); pzi = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+            }
+            float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
+#pragma unroll
+            for (int f = 0; f < 6; f += 2) { LS[f] = ld4(LSr + f * HQ + h1); LS[f + 1] = lean ? LS[f] : ld4(LSr + (f + 1) * HQ + h1); }
+            k2_cell<PML>(g, m, LS, ld4(mxx_r + h1), ld4(mzz_r + h1), ld4(mxz_r + h1), ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol),
+                         ldk4(a.cp.c33 + o, pol), ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, l, q, nA, nB, nC, nD, N);
+            st4(LSr + h1, nA); st4(LSr + HQ + h1, nB); st4(LSr + 4 * HQ + h1, nC); st4(LSr + 5 * HQ + h1, nD);
+        }
+        __syncthreads();
+        // ---- phase D: 2T/1T gathers -> cotangents of the velocity sums (pre-step), to the other set ----
+        {
+            const float* NA = LSr; const float* NB = LSr + HQ; const float* NC = LSr + 4 * HQ; const float* ND = LSr + 5 * HQ;
+            float sa[12], sc[12];
+            ldseg(NA + hs, sa); ldseg(NC + hs, sc);
+            float4 wb[2 * NN], wd[2 * NN];
+#pragma unroll
+            for (int q = 0; q < 2 * NN; ++q) {
+                wb[q] = ld4(NB + hs + (q - NN + 1) * RXH);      // (D-z)^T
+                wd[q] = ld4(ND + hs + (q - NN) * RXH);          // (D+z)^T
+            }
+            const float4 nvx = add4(xgath<NN, 1>(sa, g.c), zgath<NN>(wd, g.c));
+            const float4 nvz = add4(zgath<NN>(wb, g.c), xgath<NN, 0>(sc, g.c));
+            if (cell_ok) {
+                float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx;
+                st4(P + (size_t)(a.lcur ? P_LVX : P_LVX2) * fp, nvx); st4(P + (size_t)(a.lcur ? P_LVZ : P_LVZ2) * fp, nvz);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // group S has been consumed: refill it with the next shot while the velocity part of that shot runs
+        if (tid == 0 && pcs.valid) { b_issue_s<NN>(pcs, sst, bar + 1, th, g.ns, a.lcur, g.merge && a.tflags[pcs.tile] != 1); pcs.next_follow(g, a.w, ring); }
+    }
+    if (cell_ok) {
+        float* gp = a.gpart + (size_t)chunk * 6 * g.plane + (size_t)gz * g.ld + gx;
+        red4(gp, G11); red4(gp + g.plane, G13); red4(gp + 2 * g.plane, G33); red4(gp + 3 * g.plane, G55);
+        red4(gp + 4 * g.plane, GBX); red4(gp + 5 * g.plane, GBZ);
+    }
+}
+
+template <int NN, bool FS>
+__global__ void __launch_bounds__(NTH, 2)
+elf_b(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap th2, const __grid_constant__ CUtensorMap thh, const EGeom g, const BArgs a)
+{
+    static_assert(RPT == 1, "elf_b: one float4 group per thread");
+    static_assert(Geo<NN>::HX2 <= CPX && 2 * NN <= CPZ, "elf_b: the 2NN ring must stay inside the apron of the coefficient pack");
+    using B = GeoB<NN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bar = (uint64_t*)(smem + B::SMEM);
+    int* s_sz = (int*)(bar + 8);
+    int* s_sx = s_sz + CMAX;
+    const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    __syncthreads();
+    const Roles R(tid);
+    uint32_t par = 0;
+    const int nitems = g.ntx * g.ntz * a.w.nchunks;
+    int* ring = (int*)(bar + 4);
+    Cursor pcv, pcs;
+    pcv.wr = 0; pcs.wr = 0;
+    pcv.set(blockIdx.x, g, a.w);
+    pcs.set(blockIdx.x, g, a.w);
+    griddep_launch_dependents();
+    unsigned rd = 0;
+    bool first = true;
+    for (int item = blockIdx.x; item < nitems; item = ring[rd++ & 3u], first = false) {
+        const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
+        const int s_lo = a.w.s_begin + chunk * a.w.chunk;
+        const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
+        if (a.tflags[tile] == 1) b_tile<NN, true, FS>(&th, &th2, &thh, g, a, smem, bar, par, pcv, pcs, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        else                b_tile<NN, false, FS>(&th, &th2, &thh, g, a, smem, bar, par, pcv, pcs, ring, s_sz, s_sx, R, tid, tile, chunk, s_lo, s_hi, first);
+        __syncthreads();
+    }
+}
+
 // ---- set-up kernels ------------------------------------------------------------------------------
 // coefficient pack: eight planes [cprows][cpld] (C11,C13,C33,C55,bx,bz,bcx,bcz), logical cell (z,x) at
 // [(z+CPZ)*cpld + x+CPX], zero outside the grid
@@ -1844,7 +2232,9 @@ template <int NN> constexpr int v_smem() { return NSTAGE * Geo<NN>::V_STAGE + TA
 template <int NN> constexpr int f_smem() { return Geo<NN>::F_SMEM + TAIL_BYTES; }
 template <int NN> constexpr int k1_smem() { return NSTAGE * Geo<NN>::K1_STAGE + TAIL_SMALL; }
 template <int NN> constexpr int k2_smem() { return NSTAGE * Geo<NN>::K2_STAGE + TAIL_SMALL; }
-static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472 && 2 * (f_smem<2>() + 1024) <= 233472 && f_smem<3>() <= 232448,
+template <int NN> constexpr int b_smem() { return GeoB<NN>::SMEM + TAIL_SMALL; }
+static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472 && 2 * (f_smem<2>() + 1024) <= 233472 && f_smem<3>() <= 232448 &&
+              2 * (b_smem<2>() + 1024) <= 233472,
               "two CTAs per SM must fit in shared memory (the O(2,6) fused forward kernel runs one CTA per SM)");
 
 template <int NN> int elf_init_kernels()
@@ -1860,6 +2250,7 @@ template <int NN> int elf_init_kernels()
     rc |= elf_set_smem(elf_f<NN, false, true>, f_smem<NN>());  rc |= elf_set_smem(elf_f<NN, false, false>, f_smem<NN>());
     rc |= elf_set_smem(elf_k1<NN, true>, k1_smem<NN>());       rc |= elf_set_smem(elf_k1<NN, false>, k1_smem<NN>());
     rc |= elf_set_smem(elf_k2<NN, true>, k2_smem<NN>());       rc |= elf_set_smem(elf_k2<NN, false>, k2_smem<NN>());
+    if (NN == 2) { rc |= elf_set_smem(elf_b<2, true>, b_smem<2>()); rc |= elf_set_smem(elf_b<2, false>, b_smem<2>()); }
     if (!rc) done = true;
     return rc;
 }
@@ -1874,6 +2265,14 @@ inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid)
 }
 
 struct EArgs { const float *mt, *src_v; const int64_t *sx, *sz; };
+
+// reverse step: the fused kernel elf_b (O(2,4) only) unless ADFWI_B200_EL_ADJ_SPLIT=1 selects the two-launch form elf_k1 + elf_k2
+inline bool elf_split_adjoint()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_EL_ADJ_SPLIT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v != 0;
+}
 
 inline bool elf_split_forward()
 {
@@ -1901,7 +2300,7 @@ int elf_forward_step(const EFPlan& P, const EMaps& M, cudaStream_t st, int sb, i
         for (int k = 0; k < 5; ++k) a.rcv[k] = rcv ? rcv[k] : nullptr;
         a.w = w; a.w.counter = P.counters + (*seq)++;
         {
-            TimedLaunch tl_(KC_EL_FWD_STRESS, st);
+            TimedLaunch tl_(KC_EL_FWD_FUSED, st);
             if (P.FS) { if (save) ADFWI_CUDA(elf_launch(elf_f<NN, true, true>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a));
                         else      ADFWI_CUDA(elf_launch(elf_f<NN, true, false>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a)); }
             else      { if (save) ADFWI_CUDA(elf_launch(elf_f<NN, false, true>, grid, f_smem<NN>(), st, pdl, M.halo, M.halo2, g, a));
@@ -2025,6 +2424,23 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                 }
             }
             for (int it = t1 - 1; it >= t0; --it) {
+                if (NN == 2 && !elf_split_adjoint()) {
+                    BArgs a;
+                    a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
+                    a.nr = P.nr; a.rb = elf_bucket_ptrs(P);
+                    for (int k = 0; k < 5; ++k) a.g[k] = g_rcv[k];
+                    a.mt = ea.mt; a.sx = ea.sx; a.sz = ea.sz; a.g_src = g_src;
+                    if (seq + 1 > P.ncounters) return ADFWI_E_DIMS;
+                    a.gpart = P.gpart; a.w = w; a.w.counter = P.counters + seq++;
+                    {
+                        TimedLaunch tl_(KC_EL_ADJ_FUSED, st);
+                        if (P.FS) ADFWI_CUDA(elf_launch(elf_b<2, true>, grid, b_smem<2>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
+                        else      ADFWI_CUDA(elf_launch(elf_b<2, false>, grid, b_smem<2>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
+                    }
+                    ADFWI_LAUNCH_CHECK();
+                    lcur ^= 1;
+                    continue;
+                }
                 {
                     K1Args a;
                     a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;

@@ -502,12 +502,13 @@ def run_b200_elastic(args, wl):
         peak, peak_src = measured_peak_gbs()
         avg = {k: v[0] / v[1] for k, v in kt.items()}
         roof = None
-        adj = avg.get("el_adj_vel", 0.0) + avg.get("el_adj_stress", 0.0)
-        fwd = avg.get("el_fwd_stress", 0.0) + avg.get("el_fwd_vel", 0.0)
+        adj = avg.get("el_adj_vel", 0.0) + avg.get("el_adj_stress", 0.0) + avg.get("el_adj_fused", 0.0)
+        fwd = avg.get("el_fwd_stress", 0.0) + avg.get("el_fwd_vel", 0.0) + avg.get("el_fwd_fused", 0.0)
+        adj_name = "adjoint step (elf_b)" if "el_adj_fused" in avg else "adjoint step (elf_k1 + elf_k2)"
+        fwd_name = "forward step, recording (elf_f)" if "el_fwd_fused" in avg else "forward step, recording (elf_s + elf_v)"
         cells = batch * nzp * nxp            # one launch advances every shot of the batch by one step
         if adj > 0 and fwd > 0:
-            dom_name, dom_ms, dom_bytes = (("adjoint step (elf_k1 + elf_k2)", adj, B_EL_ADJ) if adj >= fwd else
-                                           ("forward step, recording (elf_s + elf_v)", fwd, B_EL_FWD_SAVE))
+            dom_name, dom_ms, dom_bytes = ((adj_name, adj, B_EL_ADJ) if adj >= fwd else (fwd_name, fwd, B_EL_FWD_SAVE))
             ach = dom_bytes * cells / (dom_ms * 1e-3) / 1e9
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -522,8 +523,10 @@ def run_b200_elastic(args, wl):
                     "kernel": dom_name, "avg_launch_ms": dom_ms, "algorithmic_bytes_per_cell_update": dom_bytes,
                     "cells_per_launch": cells, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                     "whole_step_frac": B_EL_GRAD_STEP / 2 * value * 1e9 / world / (peak * 1e9),
-                    "note": "the step = two launches (stress, velocity); the timed region also holds the recomputation sweep of the "
-                            "checkpointed segments, which is overhead, not counted work",
+                    "note": "forward and reverse step are one launch each (elf_f, elf_b); the timed region also holds the recomputation "
+                            "sweep of the checkpointed segments, which is overhead, not counted work",
+                    "frac_by_sweep": {"forward_recording": B_EL_FWD_SAVE * cells / (fwd * 1e-3) / 1e9 / peak,
+                                      "adjoint": B_EL_ADJ * cells / (adj * 1e-3) / 1e9 / peak},
                     "per_kernel_avg_ms": avg}
         cns, cnt = cpu_sample_size()
         cpu_v, cpu_s = cpu_gradient_sample(wl, cns, cnt)
