@@ -1568,8 +1568,20 @@ template <int NN> struct GeoB {
     static constexpr int W2 = NG + 2 * GX2;
     static constexpr int NRING2 = 4 * NN * W2 + TZ * 2 * GX2; // float4 groups of the 2NN ring
     static constexpr int V_BYTES = 6 * G::HB2, S_BYTES = 6 * G::HB, M_BYTES = 3 * G::HB;
-    static constexpr int SMEM = V_BYTES + S_BYTES + M_BYTES;
+    // per-tile coefficient tables of the ring cells (filled once per (tile, chunk), read every shot): bx, bz and the
+    // scaled PML profiles dt/2*bcx, dt/2*bcz on the 2NN ring, C11, C13, C33, C55 on the NN ring (float4 each, SoA)
+    static constexpr int T_BYTES = (4 * NRING2 + 4 * G::NRING) * 16;
+    static constexpr int SMEM = V_BYTES + S_BYTES + M_BYTES + T_BYTES;
 };
+// index of the NN-ring group (r, gi) in the 2NN-ring enumeration of ring2_cell
+template <int NN> __device__ __forceinline__ int ring2_index(int r, int gi)
+{
+    constexpr int GX2 = GeoB<NN>::GX2, W = GeoB<NN>::W2;
+    if (r < 0) return (r + 2 * NN) * W + gi + GX2;
+    if (r >= TZ) return 2 * NN * W + (r - TZ) * W + gi + GX2;
+    return 4 * NN * W + r * (2 * GX2) + (gi < 0 ? gi + GX2 : GX2 + gi - NG);
+}
+__device__ __forceinline__ float4 rcp4(const float4& a) { return make_float4(__frcp_rn(a.x), __frcp_rn(a.y), __frcp_rn(a.z), __frcp_rn(a.w)); }
 // ring float4 group i in [0, NRING2): rows [-2NN,0) and [TZ,TZ+2NN) x groups [-GX2, NG+GX2), rows [0,TZ) x the side groups
 template <int NN> __device__ __forceinline__ void ring2_cell(int i, int& r, int& gi)
 {
@@ -1637,8 +1649,24 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
     unsigned char* sst = smem + B::V_BYTES;
     float* LSr = (float*)sst;                           // 6 stress-split cotangents; rects 0, 1, 4, 5 become nA, nB, nC, nD
     float* mxx_r = (float*)(sst + B::S_BYTES); float* mzz_r = mxx_r + HQ; float* mxz_r = mxx_r + 2 * HQ;
+    float4* T_bx = (float4*)(sst + B::S_BYTES + B::M_BYTES); float4* T_bz = T_bx + B::NRING2;
+    float4* T_hx = T_bz + B::NRING2; float4* T_hz = T_hx + B::NRING2;
+    float4* T_c11 = T_hz + B::NRING2; float4* T_c13 = T_c11 + G::NRING; float4* T_c33 = T_c13 + G::NRING; float4* T_c55 = T_c33 + G::NRING;
     const int hv = (R.r0 + 2 * NN) * RX2 + R.c0 + HX2, hs = (R.r0 + NN) * RXH + R.c0 + HX;
     if (a.g_src && tid < s_hi - s_lo) { s_sz[tid] = (int)a.sz[s_lo + tid]; s_sx[tid] = (int)a.sx[s_lo + tid]; }
+    for (int i = tid; i < B::NRING2; i += NTH) {
+        int r, gi;
+        ring2_cell<NN>(i, r, gi);
+        const ptrdiff_t o = (ptrdiff_t)(Z0 + r) * g.cpld + X0 + 4 * gi;
+        T_bx[i] = ldk4(a.cp.bx + o, pol); T_bz[i] = ldk4(a.cp.bz + o, pol);
+        if (PML) { T_hx[i] = smul(g.half_dt, ldk4(a.cp.bcx + o, pol)); T_hz[i] = smul(g.half_dt, ldk4(a.cp.bcz + o, pol)); }
+    }
+    for (int i = tid; i < G::NRING; i += NTH) {
+        int r, gi;
+        ring_cell<NN>(i, r, gi);
+        const ptrdiff_t o = (ptrdiff_t)(Z0 + r) * g.cpld + X0 + 4 * gi;
+        T_c11[i] = ldk4(a.cp.c11 + o, pol); T_c13[i] = ldk4(a.cp.c13 + o, pol); T_c33[i] = ldk4(a.cp.c33 + o, pol); T_c55[i] = ldk4(a.cp.c55 + o, pol);
+    }
     const ptrdiff_t oc = (ptrdiff_t)gz * g.cpld + gx;
     const float4 C11 = ldk4(a.cp.c11 + oc, pol), C13 = ldk4(a.cp.c13 + oc, pol), C33 = ldk4(a.cp.c33 + oc, pol), C55 = ldk4(a.cp.c55 + oc, pol);
     const float4 BX = ldk4(a.cp.bx + oc, pol), BZ = ldk4(a.cp.bz + oc, pol);
@@ -1653,9 +1681,10 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
     const bool have_gs = a.nr > 0 && (a.g[0] || a.g[1] || a.g[2]);
     const bool inject_v = have_gv && a.rb.nbr[tile];
     const bool inject_s = have_gs && a.rb.nbr[tile];
+    const bool producer = tid == NTH - 32;              // lane 0 of the last warp, which has no ring cells
     if (first) {
         griddep_wait();
-        if (tid == 0) {
+        if (producer) {
             if (pcv.valid) { b_issue_v<NN>(pcv, smem, bar, th2, thh, g.ns, a.lcur, a.hist_len, a.tl, g.merge && a.tflags[pcv.tile] != 1); pcv.next(g, a.w, ring); }
             if (pcs.valid) { b_issue_s<NN>(pcs, sst, bar + 1, th, g.ns, a.lcur, g.merge && a.tflags[pcs.tile] != 1); pcs.next_follow(g, a.w, ring); }
         }
@@ -1709,6 +1738,7 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
             __syncthreads();
         }
         // ---- phase A: own-cell transpose of the velocity update on tile + 2NN ring; m1..m4 replace the split cotangents ----
+        float4 W1, W2 = zero4(), W3, W4 = zero4();
         {
             const float4 L0 = ld4(V + hv), L2 = ld4(V + 2 * HQ2 + hv);
             const float4 L1 = lean ? L0 : ld4(V + HQ2 + hv), L3 = lean ? L2 : ld4(V + 3 * HQ2 + hv);
@@ -1716,18 +1746,13 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
             k1_cell<PML>(g, mt_, L0, L1, L2, L3, ld4(lvx + hv), ld4(lvz + hv), BX, BZ, PXN, PXN, PZN, PZN, PXI, PZI,
                          w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
             st4(V + hv, m1); st4(V + HQ2 + hv, m2); st4(V + 2 * HQ2 + hv, m3); st4(V + 3 * HQ2 + hv, m4);
-            if (lean) {          // w1 == w2, w3 == w4 (dx == dz): the history holds e1 + e2 and e3 + e4
-                GBX = add4(GBX, mul4(w1, E0));
-                GBZ = add4(GBZ, mul4(w3, E2));
-            } else {
-                GBX = add4(GBX, add4(mul4(w1, E0), mul4(w2, E1)));
-                GBZ = add4(GBZ, add4(mul4(w3, E2), mul4(w4, E3)));
-            }
             if (cell_ok) {
                 float* P = a.planes + (size_t)s * g.plane + (size_t)gz * g.ld + gx + (size_t)(P_LV + 4 * (a.lcur ^ 1)) * fp;
                 st4(P, N0); st4(P + 2 * fp, N2);
                 if (!deep) { st4(P + fp, N1); st4(P + 3 * fp, N3); }
             }
+            W1 = w1; W3 = w3;
+            if (!lean) { W2 = w2; W4 = w4; }
         }
         for (int i = tid; i < B::NRING2; i += NTH) {
             int r, gi;
@@ -1735,19 +1760,26 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
             const int gzr = Z0 + r, gxr = X0 + 4 * gi;
             const int h2 = (r + 2 * NN) * RX2 + 4 * gi + HX2;
             const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
-            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
             float4 pxn = one4(), pzn = one4(), rpxd = one4(), rpzd = one4();
             if (PML) {
-                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
-                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
-                rpxd = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); rpzd = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+                const float4 hx_ = T_hx[i], hz_ = T_hz[i];
+                pxn = sub4(one4(), hx_); pzn = sub4(one4(), hz_);
+                rpxd = rcp4(add4(one4(), hx_)); rpzd = rcp4(add4(one4(), hz_));
             }
             const float4 L0 = ld4(V + h2), L2 = ld4(V + 2 * HQ2 + h2);
             const float4 L1 = lean ? L0 : ld4(V + HQ2 + h2), L3 = lean ? L2 : ld4(V + 3 * HQ2 + h2);
             float4 w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3;
-            k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + h2), ld4(lvz + h2), ldk4(a.cp.bx + o, pol), ldk4(a.cp.bz + o, pol), pxn, pxn, pzn, pzn, rpxd, rpzd,
+            k1_cell<PML>(g, m, L0, L1, L2, L3, ld4(lvx + h2), ld4(lvz + h2), T_bx[i], T_bz[i], pxn, pxn, pzn, pzn, rpxd, rpzd,
                          w1, w2, w3, w4, m1, m2, m3, m4, N0, N1, N2, N3);
             st4(V + h2, m1); st4(V + HQ2 + h2, m2); st4(V + 2 * HQ2 + h2, m3); st4(V + 3 * HQ2 + h2, m4);
+        }
+        // g_bx, g_bz (after the ring, so that the wait for the history loads does not hold up the ring cells)
+        if (lean) {              // w1 == w2, w3 == w4 (dx == dz): the history holds e1 + e2 and e3 + e4
+            GBX = add4(GBX, mul4(W1, E0));
+            GBZ = add4(GBZ, mul4(W3, E2));
+        } else {
+            GBX = add4(GBX, add4(mul4(W1, E0), mul4(W2, E1)));
+            GBZ = add4(GBZ, add4(mul4(W3, E2), mul4(W4, E3)));
         }
         __syncthreads();
         // history of the stress update (own cell): D-x vx, D-z vz, D+x vz, D+z vx (lean: the last two merged); in flight during phase B
@@ -1780,7 +1812,7 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
         fence_proxy_async();
         __syncthreads();
         // group V has been consumed: refill it with the next shot while the stress part runs
-        if (tid == 0 && pcv.valid) { b_issue_v<NN>(pcv, smem, bar, th2, thh, g.ns, a.lcur, a.hist_len, a.tl, g.merge && a.tflags[pcv.tile] != 1); pcv.next(g, a.w, ring); }
+        if (producer && pcv.valid) { b_issue_v<NN>(pcv, smem, bar, th2, thh, g.ns, a.lcur, a.hist_len, a.tl, g.merge && a.tflags[pcv.tile] != 1); pcv.next(g, a.w, ring); }
         if (inject_s) {          // 10T: cotangents of the stress records add to the sums' cotangents (tile + ring)
             for (int dz = -1; dz <= 1; ++dz) {
                 const int tz2 = tzi + dz;
@@ -1852,18 +1884,18 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
             const int gzr = Z0 + r, gxr = X0 + 4 * gi;
             const int h1 = (r + NN) * RXH + 4 * gi + HX;
             const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
-            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
             float4 pxn = one4(), pxi = one4(), pzn = one4(), pzi = one4();
             if (PML) {
-                const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
-                pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
-                pxi = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); pzi = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+                const int i2 = ring2_index<NN>(r, gi);
+                const float4 hx_ = T_hx[i2], hz_ = T_hz[i2];
+                pxn = sub4(one4(), hx_); pzn = sub4(one4(), hz_);
+                pxi = rcp4(add4(one4(), hx_)); pzi = rcp4(add4(one4(), hz_));
             }
             float4 LS[6], l[6], q[6], N[6], nA, nB, nC, nD;
 #pragma unroll
             for (int f = 0; f < 6; f += 2) { LS[f] = ld4(LSr + f * HQ + h1); LS[f + 1] = lean ? LS[f] : ld4(LSr + (f + 1) * HQ + h1); }
-            k2_cell<PML>(g, m, LS, ld4(mxx_r + h1), ld4(mzz_r + h1), ld4(mxz_r + h1), ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol),
-                         ldk4(a.cp.c33 + o, pol), ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, l, q, nA, nB, nC, nD, N);
+            k2_cell<PML>(g, m, LS, ld4(mxx_r + h1), ld4(mzz_r + h1), ld4(mxz_r + h1), T_c11[i], T_c13[i], T_c33[i], T_c55[i],
+                         pxn, pxi, pzn, pzi, l, q, nA, nB, nC, nD, N);
             st4(LSr + h1, nA); st4(LSr + HQ + h1, nB); st4(LSr + 4 * HQ + h1, nC); st4(LSr + 5 * HQ + h1, nD);
         }
         __syncthreads();
@@ -1886,9 +1918,15 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
             }
         }
         fence_proxy_async();
-        __syncthreads();
-        // group S has been consumed: refill it with the next shot while the velocity part of that shot runs
-        if (tid == 0 && pcs.valid) { b_issue_s<NN>(pcs, sst, bar + 1, th, g.ns, a.lcur, g.merge && a.tflags[pcs.tile] != 1); pcs.next_follow(g, a.w, ring); }
+        // group S has been consumed: refill it with the next shot while the velocity part of that shot runs.  Only the
+        // producer's warp waits for the other warps' phase D (named barrier 1); they go straight on to the next shot,
+        // whose phases A and B touch neither S nor anything phase D reads
+        if (tid >= NTH - 32) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory");
+            if (producer && pcs.valid) { b_issue_s<NN>(pcs, sst, bar + 1, th, g.ns, a.lcur, g.merge && a.tflags[pcs.tile] != 1); pcs.next_follow(g, a.w, ring); }
+        } else {
+            asm volatile("bar.arrive 1, %0;" ::"n"(NTH) : "memory");
+        }
     }
     if (cell_ok) {
         float* gp = a.gpart + (size_t)chunk * 6 * g.plane + (size_t)gz * g.ld + gx;
@@ -1915,10 +1953,14 @@ elf_b(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     uint32_t par = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
     int* ring = (int*)(bar + 4);
-    Cursor pcv, pcs;
-    pcv.wr = 0; pcs.wr = 0;
-    pcv.set(blockIdx.x, g, a.w);
-    pcs.set(blockIdx.x, g, a.w);
+    // the two producer cursors live in shared memory: only one thread uses them, registers are scarce
+    Cursor& pcv = *(Cursor*)(s_sx + CMAX);
+    Cursor& pcs = *((Cursor*)(s_sx + CMAX) + 1);
+    if (tid == NTH - 32) {
+        pcv.wr = 0; pcs.wr = 0;
+        pcv.set(blockIdx.x, g, a.w);
+        pcs.set(blockIdx.x, g, a.w);
+    }
     griddep_launch_dependents();
     unsigned rd = 0;
     bool first = true;
@@ -2232,7 +2274,7 @@ template <int NN> constexpr int v_smem() { return NSTAGE * Geo<NN>::V_STAGE + TA
 template <int NN> constexpr int f_smem() { return Geo<NN>::F_SMEM + TAIL_BYTES; }
 template <int NN> constexpr int k1_smem() { return NSTAGE * Geo<NN>::K1_STAGE + TAIL_SMALL; }
 template <int NN> constexpr int k2_smem() { return NSTAGE * Geo<NN>::K2_STAGE + TAIL_SMALL; }
-template <int NN> constexpr int b_smem() { return GeoB<NN>::SMEM + TAIL_SMALL; }
+template <int NN> constexpr int b_smem() { return GeoB<NN>::SMEM + TAIL_SMALL + 2 * (int)sizeof(Cursor); }
 static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472 && 2 * (f_smem<2>() + 1024) <= 233472 && f_smem<3>() <= 232448 &&
               2 * (b_smem<2>() + 1024) <= 233472,
               "two CTAs per SM must fit in shared memory (the O(2,6) fused forward kernel runs one CTA per SM)");
