@@ -290,6 +290,8 @@ struct Cursor {
     }
 };
 
+static_assert(sizeof(Cursor) == 32, "two cursors fit the last 64 bytes of TAIL_BYTES (elf_f keeps them in shared memory)");
+
 // thread roles: float4 group l, rows 2q and 2q+1 of the tile
 struct Roles {
     int q, l, r0, c0;
@@ -809,9 +811,10 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
     }
     const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
     const bool has_rcv = rcv_hi > rcv_lo;
+    const bool producer = tid == NTH - 32;              // lane 0 of the last warp, which has no ring cells
     if (first) {
         griddep_wait();
-        if (tid == 0) {
+        if (producer) {
 #pragma unroll
             for (int k = 0; k < NSTAGE; ++k)
                 if (pcv.valid) { f_issue_v<NN>(pcv, smem, bar, k, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
@@ -901,7 +904,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
         }
         __syncthreads();
         // the stress-split buffer has been consumed: refill it with the next shot while phase B runs
-        if (tid == 0 && pcs.valid) { f_issue_s<NN>(pcs, sst, bar + NSTAGE, th, g.ns, rbase); pcs.next_follow(g, a.w, ring); }
+        if (producer && pcs.valid) { f_issue_s<NN>(pcs, sst, bar + NSTAGE, th, g.ns, rbase); pcs.next_follow(g, a.w, ring); }
         if (FS && tzi == 0) {          // free-surface stress rows (:380-384) on the sums
             const int t = tid;
             if (t < RXH) {
@@ -994,7 +997,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
         }
         if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
         __syncthreads();
-        if (tid == 0 && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, k, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
+        if (producer && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, k, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 }
@@ -1019,10 +1022,14 @@ elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
     int* ring = (int*)(bar + 4);
-    Cursor pcv, pcs;
-    pcv.wr = 0; pcs.wr = 0;
-    pcv.set(blockIdx.x, g, a.w);
-    pcs.set(blockIdx.x, g, a.w);
+    // the two producer cursors live in shared memory: only one thread uses them, registers are scarce
+    Cursor& pcv = *(Cursor*)(s_sxz + CMAX);
+    Cursor& pcs = *((Cursor*)(s_sxz + CMAX) + 1);
+    if (tid == NTH - 32) {
+        pcv.wr = 0; pcs.wr = 0;
+        pcv.set(blockIdx.x, g, a.w);
+        pcs.set(blockIdx.x, g, a.w);
+    }
     griddep_launch_dependents();
     unsigned rd = 0;
     bool first = true;
