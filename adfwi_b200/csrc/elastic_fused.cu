@@ -315,6 +315,7 @@ template <int NN> __device__ __forceinline__ unsigned col_mask(int gx, int nxp)
 }
 template <int NN> __device__ __forceinline__ bool row_in(int gz, int nzp) { return gz >= NN && gz < nzp - NN; }
 
+#define ELF_SEQ() asm volatile("" ::: "memory")     // compiler-level ordering point (no instruction)
 #define ELF_WAIT_STAGE(k) do { while (!mbar_try(bar + (k), (par >> (k)) & 1u)) {} par ^= 1u << (k); } while (0)
 
 // ==========================================================================================
@@ -728,25 +729,44 @@ template <int NN> __device__ __forceinline__ void f_issue_s(const Cursor& c, uns
     for (int f = 0; f < 6; ++f) tma_load_3d(sst + f * G::HB, th, c.X0 - HX, c.Z0 - NN, (base + P_S0 + f) * ns + c.s, bar);
 }
 
-// stress update of one float4 group.  hv = index of the group in the velocity rects (pitch RX2), a[6] = the
-// split stresses of the group (in: old, out: new where the mask is set), d[4] = D-x vx, D-z vz, D+x vz, D+z vx
+// stress update of one float4 group.  hv = index of the group in the velocity rects (pitch RX2), ssp = the group in the
+// first stress-split rect, a[6] = the split stresses of the group (out: new where the mask is set, else old), d[4] = D-x vx, D-z vz, D+x vz, D+z vx
 template <int NN, bool PML>
 __device__ __forceinline__ void f_stress_cell(const EGeom& g, unsigned m, const float* vxx, const float* vxz, const float* vzx, const float* vzz,
-                                              int hv, float4* a, const float4& c11, const float4& c13, const float4& c33, const float4& c55,
+                                              int hv, const float* ssp, float4* a, const float4& c11, const float4& c13, const float4& c33, const float4& c55,
                                               const float4& pxn, const float4& pxi, const float4& pzn, const float4& pzi, float4* d)
 {
-    constexpr int RX2 = Geo<NN>::RX2;
-    float sx_[12], sz_[12];
-    ldseg2(vxx + hv, vxz + hv, sx_);
-    ldseg2(vzx + hv, vzz + hv, sz_);
-    float4 wzb[2 * NN], wzf[2 * NN];
-#pragma unroll
-    for (int q = 0; q < 2 * NN; ++q) {
-        wzb[q] = add4(ld4(vzx + hv + (q - NN) * RX2), ld4(vzz + hv + (q - NN) * RX2));
-        wzf[q] = add4(ld4(vxx + hv + (q - NN + 1) * RX2), ld4(vxz + hv + (q - NN + 1) * RX2));
+    constexpr int RX2 = Geo<NN>::RX2, HQs = Geo<NN>::HB / 4;
+    // one derivative at a time (ELF_SEQ keeps the compiler from hoisting all 24 shared-memory loads to the top):
+    // the kernel runs at the 128-register cap and every spilled value comes back at L2 latency
+    {
+        float sx_[12];
+        ldseg2(vxx + hv, vxz + hv, sx_);
+        d[0] = xdiff<NN, 0>(sx_, g.c);
     }
-    d[0] = xdiff<NN, 0>(sx_, g.c); d[2] = xdiff<NN, 1>(sz_, g.c);
-    d[1] = zdiff<NN>(wzb, g.c); d[3] = zdiff<NN>(wzf, g.c);
+    ELF_SEQ();
+    {
+        float sz_[12];
+        ldseg2(vzx + hv, vzz + hv, sz_);
+        d[2] = xdiff<NN, 1>(sz_, g.c);
+    }
+    ELF_SEQ();
+    {
+        float4 wzb[2 * NN];
+#pragma unroll
+        for (int q = 0; q < 2 * NN; ++q) wzb[q] = add4(ld4(vzx + hv + (q - NN) * RX2), ld4(vzz + hv + (q - NN) * RX2));
+        d[1] = zdiff<NN>(wzb, g.c);
+    }
+    ELF_SEQ();
+    {
+        float4 wzf[2 * NN];
+#pragma unroll
+        for (int q = 0; q < 2 * NN; ++q) wzf[q] = add4(ld4(vxx + hv + (q - NN + 1) * RX2), ld4(vxz + hv + (q - NN + 1) * RX2));
+        d[3] = zdiff<NN>(wzf, g.c);
+    }
+    ELF_SEQ();
+#pragma unroll
+    for (int f = 0; f < 6; ++f) a[f] = ld4(ssp + f * HQs);
     float4 n0, n1, n2, n3, n4, n5;
     if (PML) {
         n0 = mul4(add4(mul4(pxn, a[0]), smul(g.dt_dx, mul4(c11, d[0]))), pxi);
@@ -853,9 +873,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
             const int hv = (r + 2 * NN) * RX2 + R.c0 + HX2, hs = (r + NN) * RXH + R.c0 + HX;
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
             float4 sp[6], d[4];
-#pragma unroll
-            for (int f = 0; f < 6; ++f) sp[f] = ld4(ssp + f * HQ + hs);
-            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, sp, C11[j], C13[j], C33[j], C55[j], PXN[j], PXI[j], PZN[j], PZI[j], d);
+            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, sp, C11[j], C13[j], C33[j], C55[j], PXN[j], PXI[j], PZN[j], PZI[j], d);
             if (szs == gz && !(FS && gz < NN)) {
                 const int dc = sxs - gx;
                 if (dc >= 0 && dc < 4) { addc4(sp[0], dc, sxx); addc4(sp[1], dc, sxx); addc4(sp[2], dc, szz); addc4(sp[3], dc, szz); addc4(sp[4], dc, sxz); addc4(sp[5], dc, sxz); }
@@ -892,9 +910,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                 pxi = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); pzi = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
             }
             float4 sp[6], d[4];
-#pragma unroll
-            for (int f = 0; f < 6; ++f) sp[f] = ld4(ssp + f * HQ + hs);
-            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol),
+            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol),
                                    ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, d);
             if (szs == gzr && !(FS && gzr < NN)) {
                 const int dc = sxs - gxr;
@@ -925,17 +941,29 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
         for (int j = 0; j < RPT; ++j) {
             const int r = R.r0 + j, gz = gz0 + j;
             const int hv = (r + 2 * NN) * RX2 + R.c0 + HX2, hs = (r + NN) * RXH + R.c0 + HX;
-            float sxx_[12], sxz_[12];
-            ldseg(txx + hs, sxx_);
-            ldseg(txz + hs, sxz_);
-            float4 wzb[2 * NN], wzf[2 * NN];
-#pragma unroll
-            for (int q = 0; q < 2 * NN; ++q) {
-                wzb[q] = ld4(txz + hs + (q - NN) * RXH);
-                wzf[q] = ld4(tzz + hs + (q - NN + 1) * RXH);
+            float4 dxf_txx, dxb_txz, dzb_txz, dzf_tzz;
+            {
+                float sxx_[12];
+                ldseg(txx + hs, sxx_);
+                dxf_txx = xdiff<NN, 1>(sxx_, g.c);
             }
-            const float4 dxf_txx = xdiff<NN, 1>(sxx_, g.c), dxb_txz = xdiff<NN, 0>(sxz_, g.c);
-            const float4 dzb_txz = zdiff<NN>(wzb, g.c), dzf_tzz = zdiff<NN>(wzf, g.c);
+            ELF_SEQ();
+            {
+                float sxz_[12];
+                ldseg(txz + hs, sxz_);
+                dxb_txz = xdiff<NN, 0>(sxz_, g.c);
+            }
+            ELF_SEQ();
+            {
+                float4 wzb[2 * NN], wzf[2 * NN];
+#pragma unroll
+                for (int q = 0; q < 2 * NN; ++q) {
+                    wzb[q] = ld4(txz + hs + (q - NN) * RXH);
+                    wzf[q] = ld4(tzz + hs + (q - NN + 1) * RXH);
+                }
+                dzb_txz = zdiff<NN>(wzb, g.c); dzf_tzz = zdiff<NN>(wzf, g.c);
+            }
+            ELF_SEQ();
             float4 q0 = ld4(vxx + hv), q1 = ld4(vxz + hv), q2 = ld4(vzx + hv), q3 = ld4(vzz + hv);
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
             float4 n0, n1, n2, n3;
