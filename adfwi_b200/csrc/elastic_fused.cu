@@ -190,6 +190,9 @@ __device__ __forceinline__ float4 fdivs(const float4& a, float b, float rb)
     return make_float4(fdiv1(a.x, b, rb), fdiv1(a.y, b, rb), fdiv1(a.z, b, rb), fdiv1(a.w, b, rb));
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void opaque4(float4& v) { asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)); }
+// correctly rounded reciprocals: the same bits as 1.0f / a under -prec-div=true
+__device__ __forceinline__ float4 rcp4(const float4& a) { return make_float4(__frcp_rn(a.x), __frcp_rn(a.y), __frcp_rn(a.z), __frcp_rn(a.w)); }
 __device__ __forceinline__ float4 one4() { return make_float4(1.f, 1.f, 1.f, 1.f); }
 __device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 // per-component select: bit x of m set -> a, else b
@@ -789,12 +792,16 @@ __device__ __forceinline__ void f_stress_cell(const EGeom& g, unsigned m, const 
 
 template <int NN, bool PML, bool FS, bool SAVE>
 __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap* th2, const EGeom& g, const FArgs& a,
-                                       unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pcv, Cursor& pcs, int* ring,
+                                       unsigned char* smem, uint64_t* bar, volatile int* ctl, Cursor& pcv, Cursor& pcs, int* ring,
                                        int* s_sz, int* s_sx, float* s_sxx, float* s_szz, float* s_sxz,
                                        const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
 {
     using G = Geo<NN>;
     constexpr int RX2 = G::RX2, HX2 = G::HX2, HQ = G::HB / 4, HQ2 = G::HB2 / 4;
+    // loop control of the shot walk lives in the warp's slot of shared memory (ctl[0] = first shot, ctl[1] = end,
+    // ctl[2] = shots this CTA has processed): at the 128-register cap the compiler spills exactly these, and a spilled
+    // value comes back at L2 latency on the critical path of every shot
+    ctl[0] = s_lo; ctl[1] = s_hi;
     const uint64_t pol = l2_keep_policy();
     const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
     const int X0 = txi * TX, Z0 = tzi * TZ;
@@ -815,19 +822,18 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
         s_sz[tid] = (int)a.sz[s]; s_sx[tid] = (int)a.sx[s];
         s_sxx[tid] = (-(M[0] / 2.0f)) * v; s_szz[tid] = (-(M[8] / 2.0f)) * v; s_sxz[tid] = (-(M[2] / 2.0f)) * v;
     }
-    float4 C11[RPT], C13[RPT], C33[RPT], C55[RPT], DBX[RPT], DBZ[RPT], PXN[RPT], PZN[RPT], PXD[RPT], PZD[RPT], PXI[RPT], PZI[RPT];
+    // PML tiles keep only the scaled profiles dt/2*bcx, dt/2*bcz of the thread's cells; 1 -+ h and the correctly rounded
+    // 1/(1 + h) (same bits as the division) are rebuilt where they are used: six float4 of factors held across the
+    // walk were what pushed the kernel over the 128-register cap
+    float4 C11[RPT], C13[RPT], C33[RPT], C55[RPT], DBX[RPT], DBZ[RPT], HBX[RPT], HBZ[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         const ptrdiff_t o = (ptrdiff_t)(gz0 + j) * g.cpld + gx;
         C11[j] = ldk4(a.cp.c11 + o, pol); C13[j] = ldk4(a.cp.c13 + o, pol);
         C33[j] = ldk4(a.cp.c33 + o, pol); C55[j] = ldk4(a.cp.c55 + o, pol);
         DBX[j] = smul(g.dt, ldk4(a.cp.bx + o, pol)); DBZ[j] = smul(g.dt, ldk4(a.cp.bz + o, pol));
-        if (PML) {
-            const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
-            PXD[j] = add4(one4(), smul(g.half_dt, bx_)); PZD[j] = add4(one4(), smul(g.half_dt, bz_));
-            PXN[j] = sub4(one4(), smul(g.half_dt, bx_)); PZN[j] = sub4(one4(), smul(g.half_dt, bz_));
-            PXI[j] = div4(one4(), PXD[j]); PZI[j] = div4(one4(), PZD[j]);
-        } else { PXD[j] = PZD[j] = PXN[j] = PZN[j] = PXI[j] = PZI[j] = one4(); }
+        if (PML) { HBX[j] = smul(g.half_dt, ldk4(a.cp.bcx + o, pol)); HBZ[j] = smul(g.half_dt, ldk4(a.cp.bcz + o, pol)); }
+        else { HBX[j] = HBZ[j] = zero4(); }
     }
     const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
     const bool has_rcv = rcv_hi > rcv_lo;
@@ -843,12 +849,14 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
     }
     __syncthreads();
 
-    for (int s = s_lo; s < s_hi; ++s) {
-        const int k = stage;
+    for (int s = s_lo; s < ctl[1]; ++s) {
+        const int n = ctl[2];
+        const int k = n & 1;           // V stage; its barrier completes every second shot, the S barrier every shot
         float* vxx = (float*)(smem + k * G::F_VSTAGE); float* vxz = vxx + HQ2; float* vzx = vxx + 2 * HQ2; float* vzz = vxx + 3 * HQ2;
-        const int szs = s_sz[s - s_lo], sxs = s_sx[s - s_lo];
-        const float sxx = s_sxx[s - s_lo], szz = s_szz[s - s_lo], sxz = s_sxz[s - s_lo];
-        ELF_WAIT_STAGE(k);
+        const int si = s - ctl[0];
+        const int szs = s_sz[si], sxs = s_sx[si];
+        const float sxx = s_sxx[si], szz = s_szz[si], sxz = s_sxz[si];
+        while (!mbar_try(bar + k, (unsigned)(n >> 1) & 1u)) {}
         if (FS && tzi == 0) {          // free-surface velocity rows (:399-402) formed in the staged rects (see elf_s)
             const int t = tid;
             if (t >= HX2 - NN && t < HX2 + TX + NN) {
@@ -865,7 +873,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
             }
             __syncthreads();
         }
-        ELF_WAIT_STAGE(NSTAGE);
+        while (!mbar_try(bar + NSTAGE, (unsigned)n & 1u)) {}
         // ---- phase A: stress on the tile (coefficients in registers) and on the ring (coefficients from L2) ----
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
@@ -873,7 +881,13 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
             const int hv = (r + 2 * NN) * RX2 + R.c0 + HX2, hs = (r + NN) * RXH + R.c0 + HX;
             const unsigned m = row_in<NN>(gz, g.nzp) ? cm : 0u;
             float4 sp[6], d[4];
-            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, sp, C11[j], C13[j], C33[j], C55[j], PXN[j], PXI[j], PZN[j], PZI[j], d);
+            float4 pxn = one4(), pxi = one4(), pzn = one4(), pzi = one4();
+            if (PML) {
+                float4 hx = HBX[j], hz = HBZ[j];
+                opaque4(hx); opaque4(hz);          // keeps the factors from being hoisted out of the shot loop (back into registers)
+                pxn = sub4(one4(), hx); pzn = sub4(one4(), hz); pxi = rcp4(add4(one4(), hx)); pzi = rcp4(add4(one4(), hz));
+            }
+            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, sp, C11[j], C13[j], C33[j], C55[j], pxn, pxi, pzn, pzi, d);
             if (szs == gz && !(FS && gz < NN)) {
                 const int dc = sxs - gx;
                 if (dc >= 0 && dc < 4) { addc4(sp[0], dc, sxx); addc4(sp[1], dc, sxx); addc4(sp[2], dc, szz); addc4(sp[3], dc, szz); addc4(sp[4], dc, sxz); addc4(sp[5], dc, sxz); }
@@ -973,18 +987,23 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                 dg.add(A0); dg.add(A1); dg.add(A2); dg.add(A3);
                 float4 t0 = fdivs(A0, g.dx, g.rdx), t1 = fdivs(A1, g.dz, g.rdz), t2 = fdivs(A2, g.dx, g.rdx), t3 = fdivs(A3, g.dz, g.rdz);
                 if (PML) {
-                    const float4 B0 = add4(mul4(PXN[j], q0), t0), B1 = add4(mul4(PZN[j], q1), t1);
-                    const float4 B2 = add4(mul4(PXN[j], q2), t2), B3 = add4(mul4(PZN[j], q3), t3);
+                    float4 hx = HBX[j], hz = HBZ[j];
+                    opaque4(hx); opaque4(hz);
+                    const float4 pxn = sub4(one4(), hx), pzn = sub4(one4(), hz), pxd = add4(one4(), hx), pzd = add4(one4(), hz);
+                    const float4 B0 = add4(mul4(pxn, q0), t0), B1 = add4(mul4(pzn, q1), t1);
+                    const float4 B2 = add4(mul4(pxn, q2), t2), B3 = add4(mul4(pzn, q3), t3);
                     dg.add(B0); dg.add(B1); dg.add(B2); dg.add(B3);
-                    n0 = fdiv4(B0, PXD[j], PXI[j]); n1 = fdiv4(B1, PZD[j], PZI[j]); n2 = fdiv4(B2, PXD[j], PXI[j]); n3 = fdiv4(B3, PZD[j], PZI[j]);
+                    const float4 pxi = rcp4(pxd), pzi = rcp4(pzd);
+                    n0 = fdiv4(B0, pxd, pxi); n1 = fdiv4(B1, pzd, pzi); n2 = fdiv4(B2, pxd, pxi); n3 = fdiv4(B3, pzd, pzi);
                 } else {
                     n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
                 }
                 if (!dg.ok()) {
                     t0 = ieee_divs(A0, g.dx); t1 = ieee_divs(A1, g.dz); t2 = ieee_divs(A2, g.dx); t3 = ieee_divs(A3, g.dz);
                     if (PML) {
-                        n0 = ieee_div4(add4(mul4(PXN[j], q0), t0), PXD[j]); n1 = ieee_div4(add4(mul4(PZN[j], q1), t1), PZD[j]);
-                        n2 = ieee_div4(add4(mul4(PXN[j], q2), t2), PXD[j]); n3 = ieee_div4(add4(mul4(PZN[j], q3), t3), PZD[j]);
+                        const float4 pxn = sub4(one4(), HBX[j]), pzn = sub4(one4(), HBZ[j]), pxd = add4(one4(), HBX[j]), pzd = add4(one4(), HBZ[j]);
+                        n0 = ieee_div4(add4(mul4(pxn, q0), t0), pxd); n1 = ieee_div4(add4(mul4(pzn, q1), t1), pzd);
+                        n2 = ieee_div4(add4(mul4(pxn, q2), t2), pxd); n3 = ieee_div4(add4(mul4(pzn, q3), t3), pzd);
                     } else {
                         n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
                     }
@@ -1025,8 +1044,8 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
         }
         if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
         __syncthreads();
-        if (producer && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, k, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
-        stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
+        if (producer && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, ctl[2] & 1, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
+        ctl[2] = ctl[2] + 1;
     }
 }
 
@@ -1046,8 +1065,9 @@ elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     if (tid == 0) { for (int k = 0; k < NSTAGE + 1; ++k) mbar_init(bar + k, 1); }
     __syncthreads();
     const Roles R(tid);
-    uint32_t par = 0;
-    int stage = 0;
+    static_assert(NSTAGE == 2, "f_tile derives stage and barrier parities from the shot counter");
+    volatile int* ctl = (volatile int*)(smem + G::F_SMEM + TAIL_BYTES) + (tid >> 5) * 4;
+    ctl[2] = 0;
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
     int* ring = (int*)(bar + 4);
     // the two producer cursors live in shared memory: only one thread uses them, registers are scarce
@@ -1065,8 +1085,8 @@ elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        if (a.tflags[tile] == 1) f_tile<NN, true, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
-        else                f_tile<NN, false, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        if (a.tflags[tile] == 1) f_tile<NN, true, FS, SAVE>(&th, &th2, g, a, smem, bar, ctl, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        else                f_tile<NN, false, FS, SAVE>(&th, &th2, g, a, smem, bar, ctl, pcv, pcs, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -1616,7 +1636,7 @@ template <int NN> __device__ __forceinline__ int ring2_index(int r, int gi)
     if (r >= TZ) return 2 * NN * W + (r - TZ) * W + gi + GX2;
     return 4 * NN * W + r * (2 * GX2) + (gi < 0 ? gi + GX2 : GX2 + gi - NG);
 }
-__device__ __forceinline__ float4 rcp4(const float4& a) { return make_float4(__frcp_rn(a.x), __frcp_rn(a.y), __frcp_rn(a.z), __frcp_rn(a.w)); }
+
 // ring float4 group i in [0, NRING2): rows [-2NN,0) and [TZ,TZ+2NN) x groups [-GX2, NG+GX2), rows [0,TZ) x the side groups
 template <int NN> __device__ __forceinline__ void ring2_cell(int i, int& r, int& gi)
 {
@@ -2306,7 +2326,7 @@ template <typename K> int elf_set_smem(K kern, int bytes) { return (int)cudaFunc
 
 template <int NN> constexpr int s_smem() { return NSTAGE * Geo<NN>::S_STAGE + TAIL_BYTES; }
 template <int NN> constexpr int v_smem() { return NSTAGE * Geo<NN>::V_STAGE + TAIL_SMALL; }
-template <int NN> constexpr int f_smem() { return Geo<NN>::F_SMEM + TAIL_BYTES; }
+template <int NN> constexpr int f_smem() { return Geo<NN>::F_SMEM + TAIL_BYTES + (NTH / 32) * 16; }
 template <int NN> constexpr int k1_smem() { return NSTAGE * Geo<NN>::K1_STAGE + TAIL_SMALL; }
 template <int NN> constexpr int k2_smem() { return NSTAGE * Geo<NN>::K2_STAGE + TAIL_SMALL; }
 template <int NN> constexpr int b_smem() { return GeoB<NN>::SMEM + TAIL_SMALL + 2 * (int)sizeof(Cursor); }
