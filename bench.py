@@ -35,9 +35,9 @@ WORKLOADS = {
                desc="iso-acoustic Marmousi2 example 88x200 (148x260 padded), nt=1600"),
     "C2": dict(nz=350, nx=1700, dx=10.0, dt=1e-3, nt=4000, f0=10.0, nabc=50, shots8=240, nr=1700, batch=10,
                desc="iso-acoustic Marmousi2 full-res 350x1700 (450x1800 padded), nt=4000, 240 shots / 8 GPUs"),
-    "C3": dict(kind="elastic", nz=350, nx=1700, dx=10.0, dt=1e-3, nt=4000, f0=10.0, nabc=50, shots8=240, nr=1700, batch=15, z_sr=10,
+    "C3": dict(kind="elastic", nz=350, nx=1700, dx=10.0, dt=1e-3, nt=4000, f0=10.0, nabc=50, shots8=240, nr=1700, batch=30, z_sr=10,
                desc="iso-elastic Marmousi2 350x1700 (402x1800 padded), split-PML O(2,4), free surface, nt=4000, vp/vs/rho gradients, 240 shots / 8 GPUs"),
-    "C4": dict(kind="elastic", nz=320, nx=720, dx=2.5, dt=2.5e-4, nt=4000, f0=30.0, nabc=50, shots8=120, nr=720, batch=5, z_sr=10, vti=True,
+    "C4": dict(kind="elastic", nz=320, nx=720, dx=2.5, dt=2.5e-4, nt=4000, f0=30.0, nabc=50, shots8=120, nr=720, batch=15, z_sr=10, vti=True,
                desc="VTI-elastic 320x720 (372x820 padded), split-PML O(2,4), free surface, nt=4000, eps/delta gradients, 120 shots / 8 GPUs"),
     "C5": dict(nz=2048, nx=8192, dx=5.0, dt=5e-4, nt=1000, f0=15.0, nabc=50, shots8=8 * 2, nr=8192, batch=2,
                desc="synthetic acoustic 2048x8192 (2148x8292 padded), 1000-step slice of nt=8000, 2 shots/GPU"),
@@ -514,9 +514,11 @@ def run_b200_elastic(args, wl):
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tpath):
                 try:
+                    # the ncu capture is taken on a shortened run (tools/profile_r01s.sh); DRAM bytes of a launch
+                    # scale with the cells it advances, so the captured figure is rescaled to this run's launch size
                     tj = json.load(open(tpath)).get(args.workload, {})
-                    if tj.get("batch") == batch:
-                        traffic = tj.get("el_adj" if adj >= fwd else "el_fwd")
+                    if tj.get("cells_per_launch"):
+                        traffic = int(tj["el_adj" if adj >= fwd else "el_fwd"] * cells / tj["cells_per_launch"])
                 except Exception:
                     traffic = None
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
