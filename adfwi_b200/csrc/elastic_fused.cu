@@ -734,9 +734,9 @@ template <int NN> __device__ __forceinline__ void f_issue_s(const Cursor& c, uns
 
 // stress update of one float4 group.  hv = index of the group in the velocity rects (pitch RX2), ssp = the group in the
 // first stress-split rect, a[6] = the split stresses of the group (out: new where the mask is set, else old), d[4] = D-x vx, D-z vz, D+x vz, D+z vx
-template <int NN, bool PML>
+template <int NN, bool PML, bool WAIT_S = false>
 __device__ __forceinline__ void f_stress_cell(const EGeom& g, unsigned m, const float* vxx, const float* vxz, const float* vzx, const float* vzz,
-                                              int hv, const float* ssp, float4* a, const float4& c11, const float4& c13, const float4& c33, const float4& c55,
+                                              int hv, const float* ssp, uint64_t* sbar, uint32_t sparity, float4* a, const float4& c11, const float4& c13, const float4& c33, const float4& c55,
                                               const float4& pxn, const float4& pxi, const float4& pzn, const float4& pzi, float4* d)
 {
     constexpr int RX2 = Geo<NN>::RX2, HQs = Geo<NN>::HB / 4;
@@ -768,6 +768,9 @@ __device__ __forceinline__ void f_stress_cell(const EGeom& g, unsigned m, const 
         d[3] = zdiff<NN>(wzf, g.c);
     }
     ELF_SEQ();
+    // the stress splits (single TMA buffer, refilled during phase B of the previous shot) are needed only now: the
+    // four derivatives above hide part of that load's latency
+    if (WAIT_S) { while (!mbar_try(sbar, sparity)) {} }
 #pragma unroll
     for (int f = 0; f < 6; ++f) a[f] = ld4(ssp + f * HQs);
     float4 n0, n1, n2, n3, n4, n5;
@@ -873,7 +876,6 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
             }
             __syncthreads();
         }
-        while (!mbar_try(bar + NSTAGE, (unsigned)n & 1u)) {}
         // ---- phase A: stress on the tile (coefficients in registers) and on the ring (coefficients from L2) ----
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
@@ -887,7 +889,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                 opaque4(hx); opaque4(hz);          // keeps the factors from being hoisted out of the shot loop (back into registers)
                 pxn = sub4(one4(), hx); pzn = sub4(one4(), hz); pxi = rcp4(add4(one4(), hx)); pzi = rcp4(add4(one4(), hz));
             }
-            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, sp, C11[j], C13[j], C33[j], C55[j], pxn, pxi, pzn, pzi, d);
+            f_stress_cell<NN, PML, true>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, bar + NSTAGE, (unsigned)n & 1u, sp, C11[j], C13[j], C33[j], C55[j], pxn, pxi, pzn, pzi, d);
             if (szs == gz && !(FS && gz < NN)) {
                 const int dc = sxs - gx;
                 if (dc >= 0 && dc < 4) { addc4(sp[0], dc, sxx); addc4(sp[1], dc, sxx); addc4(sp[2], dc, szz); addc4(sp[3], dc, szz); addc4(sp[4], dc, sxz); addc4(sp[5], dc, sxz); }
@@ -924,7 +926,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                 pxi = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); pzi = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
             }
             float4 sp[6], d[4];
-            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol),
+            f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, nullptr, 0u, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol),
                                    ldk4(a.cp.c55 + o, pol), pxn, pxi, pzn, pzi, d);
             if (szs == gzr && !(FS && gzr < NN)) {
                 const int dc = sxs - gxr;
