@@ -52,6 +52,7 @@ PtrArray6 = C.c_void_p * 6
 SYMBOLS = [
     "adfwi_acoustic_workspace_bytes", "adfwi_acoustic_group_size", "adfwi_acoustic_forward", "adfwi_acoustic_backward",
     "adfwi_elastic_workspace_bytes", "adfwi_elastic_forward", "adfwi_elastic_backward",
+    "adfwi_gradproc_workspace_bytes", "adfwi_gradproc_forward", "adfwi_gradproc_smooth2d",
     "adfwi_strerror", "adfwi_abi_version", "adfwi_launch_count",
     "adfwi_timing_enable", "adfwi_timing_collect",
 ]
@@ -64,8 +65,22 @@ KERNEL_CLASSES = [
 ]
 
 
+class GradProcDesc(C.Structure):
+    """adfwi_gradproc_desc of include/adfwi_b200.h"""
+    _fields_ = [("nz", C.c_int32), ("nx", C.c_int32), ("grad_mute", C.c_int32), ("grad_smooth", C.c_int32),
+                ("taper_marine", C.c_int32), ("smooth_below_mute", C.c_int32), ("norm_grad", C.c_int32),
+                ("use_illumination", C.c_int32), ("illum_span", C.c_int32), ("reserved", C.c_int32),
+                ("thred", C.c_double), ("vmax", C.c_double)]
+
+
 def bind(lib):
     vp = C.c_void_p
+    lib.adfwi_gradproc_workspace_bytes.restype = C.c_size_t
+    lib.adfwi_gradproc_workspace_bytes.argtypes = [C.POINTER(GradProcDesc)]
+    lib.adfwi_gradproc_forward.restype = C.c_int
+    lib.adfwi_gradproc_forward.argtypes = [C.POINTER(GradProcDesc), vp, vp, vp, vp, C.POINTER(C.c_int), vp, C.c_size_t, vp]
+    lib.adfwi_gradproc_smooth2d.restype = C.c_int
+    lib.adfwi_gradproc_smooth2d.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]
     lib.adfwi_acoustic_workspace_bytes.restype = C.c_size_t
     lib.adfwi_acoustic_workspace_bytes.argtypes = [C.POINTER(AcousticDesc)]
     lib.adfwi_acoustic_group_size.restype = C.c_int

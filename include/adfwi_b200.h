@@ -149,6 +149,39 @@ int adfwi_elastic_backward(const adfwi_elastic_desc* desc, const float* const* c
                            const float* const* g_rcv, float* const* g_coef, float* g_src_v,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradient post-processing.  Replaces GradProcessor.forward
+ * (ADFWI/propagator/gradient_process.py:88-135: mute taper :97-98 / grad_taper :51-72, mask :101-107,
+ * illumination preconditioner :117-122 with smooth2d :30-49, smoothing :125-131, max-normalisation
+ * :134-135) and the device->host->device round trip around it (ADFWI/fwi/acoustic_fwi.py:171-177).
+ * The reference computes in numpy float64 on the host; this entry point does the same arithmetic in
+ * float64 on the device (the Gaussian filter of smooth2d is applied as its two 1-D factors).
+ * `grad` is the float32 gradient plane [nz][nx] (what `model.vp.grad` holds), `forw` the float32
+ * illumination plane or NULL, `mask` a float64 plane or NULL.  `out` receives nz*nx doubles.
+ * `*out_is_f32_host` (host pointer, may be NULL) is set to 1 when numpy's promotion rules make the
+ * reference return float32 (no illumination division and no whole-plane smoothing): the values in
+ * `out` are then exactly representable in float32.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nz, nx;
+    int32_t grad_mute;        /* rows / columns of the taper, 0 = none (:97) */
+    int32_t grad_smooth;      /* span of the final smoothing, 0 = none (:125) */
+    int32_t taper_marine;     /* 1: marine_or_land in {'Marine','Offshore'} (grad_taper's own, case-sensitive test :55) */
+    int32_t smooth_below_mute;/* 1: marine_or_land in {'marine','offshore'}: smooth rows >= grad_mute only (:127-128) */
+    int32_t norm_grad;        /* :134 */
+    int32_t use_illumination; /* forw_illumination and forw given (:117) */
+    int32_t illum_span;       /* 40, or min(nz,nx)/2 on small grids (:112-115) */
+    int32_t reserved;
+    double  thred;            /* 0.0 marine/offshore, 0.001 land/onshore (:90-95) */
+    double  vmax;             /* value of the (float32) scalar the reference passes */
+} adfwi_gradproc_desc;
+
+size_t adfwi_gradproc_workspace_bytes(const adfwi_gradproc_desc* desc);
+int adfwi_gradproc_forward(const adfwi_gradproc_desc* desc, const float* grad, const float* forw, const double* mask,
+                           double* out, int* out_is_f32_host, void* workspace, size_t workspace_bytes, void* stream);
+/* smooth2d alone (gradient_process.py:30-49) on a float64 plane; workspace as above with nz, nx set */
+int adfwi_gradproc_smooth2d(int nz, int nx, int span, const double* in, double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* misc */
 const char* adfwi_strerror(int code);
 int adfwi_abi_version(void);
