@@ -147,7 +147,6 @@ F4OP(div4, x / y)
 #undef F4OP
 __device__ __forceinline__ float4 muls(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float4 smul(float s, const float4& a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
-__device__ __forceinline__ float4 divs(const float4& a, float s) { return make_float4(a.x / s, a.y / s, a.z / s, a.w / s); }
 // Correctly rounded a / b from a precomputed correctly rounded reciprocal rb = RN(1/b): one multiply and two
 // Newton corrections with exact FMA remainders.  After the first correction q is a faithful rounding of a/b,
 // so the second one returns RN(a/b) (Markstein's theorem) -- the same bits as the IEEE division of the eager
@@ -194,7 +193,6 @@ __device__ __forceinline__ void opaque4(float4& v) { asm volatile("" : "+f"(v.x)
 // correctly rounded reciprocals: the same bits as 1.0f / a under -prec-div=true
 __device__ __forceinline__ float4 rcp4(const float4& a) { return make_float4(__frcp_rn(a.x), __frcp_rn(a.y), __frcp_rn(a.z), __frcp_rn(a.w)); }
 __device__ __forceinline__ float4 one4() { return make_float4(1.f, 1.f, 1.f, 1.f); }
-__device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 // per-component select: bit x of m set -> a, else b
 __device__ __forceinline__ float4 sel4(unsigned m, const float4& a, const float4& b)
 { return make_float4((m & 1u) ? a.x : b.x, (m & 2u) ? a.y : b.y, (m & 4u) ? a.z : b.z, (m & 8u) ? a.w : b.w); }

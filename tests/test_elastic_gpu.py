@@ -135,3 +135,16 @@ def test_fused_large_grid_matches_generic(order, shape):
         for k in PLANES:
             e = rel_l2(out[False][1][k].cpu().numpy(), out[True][1][k].cpu().numpy())
             assert e < 2e-5, (order, fs, k, e)
+
+
+def test_two_launch_reverse_step_fallback(golden_dir):
+    """ADFWI_B200_EL_ADJ_SPLIT=1 keeps the pair elf_k1 + elf_k2 as the O(2,4) reverse step (the switch is read once
+    per process, so the check runs in a child process): same golden gradients."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ADFWI_B200_EL_ADJ_SPLIT="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "(test_golden_records_and_gradients and pml_o4 and cfg0) or (fused_large and shape1-4)"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
