@@ -74,3 +74,22 @@ def test_diff_coef_bits():
     for NN in (2, 3):
         assert np.array_equal(np.array(ek.diff_coef(NN), dtype=np.float32), O.diff_coef(NN))
     assert abs(ek.diff_coef(3)[1] - (-25.0 / 384.0)) < 1e-8
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the driver's reference arm) runs on the host only: one JSON line with the keys the
+    contract names, timed on the oracle port."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Gcell-updates/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
