@@ -71,3 +71,44 @@ def elastic_gradient(propagator, obs: dict, shots: Optional[Sequence[int]] = Non
         fw = rec["forward_wavefield_vz"]
         illum = fw if illum is None else illum + fw
     return total, illum
+
+
+def acoustic_fwi(propagator, model, optimizer, scheduler, obs_p: torch.Tensor, iterations: int, batch_size: Optional[int] = None,
+                 gradient_processor=None, waveform_normalize: bool = True, misfit: Optional[Callable] = None,
+                 checkpoint_segments: int = 1):
+    """The iteration loop of ``AcousticFWI.forward`` (ADFWI/fwi/acoustic_fwi.py:128-200) with every step on the device:
+    shot batches -> per-trace max normalisation (:149-150) -> misfit -> backward -> gradient post-processing
+    (``adfwi_b200.propagator.GradProcessor``; the reference copies gradient and illumination to the host here,
+    :171-177) -> ``optimizer.step()`` / ``scheduler.step()``.  ``optimizer`` / ``scheduler`` are ordinary torch objects over
+    ``model.parameters()``; ``misfit(syn, obs)`` defaults to the L2 waveform misfit with dt = 1 as in the examples.
+    Returns {"loss": [..], "grad": [processed vp gradient per iteration]} (what the reference caches, :186-189)."""
+    misfit = misfit or (lambda syn, obs: l2_waveform_misfit(obs, syn, 1.0))
+    obs = obs_p
+    if waveform_normalize:
+        obs = obs / torch.max(torch.abs(obs), dim=1, keepdim=True).values
+    n_shots = propagator.src_n
+    hist = {"loss": [], "grad": []}
+    for _ in range(iterations):
+        optimizer.zero_grad()
+        loss_it, forw = 0.0, None
+        for pos in shot_batches(n_shots, batch_size):
+            rec = propagator.forward(shot_index=pos, checkpoint_segments=checkpoint_segments)
+            fw = rec["forward_wavefield_p"]
+            forw = fw if forw is None else forw + fw
+            syn = rec["p"]
+            if waveform_normalize:
+                syn = syn / torch.max(torch.abs(syn), dim=1, keepdim=True).values
+            loss = misfit(syn, obs[pos])
+            loss.backward()
+            loss_it += float(loss.item())
+        grads = model.vp.grad
+        if gradient_processor is not None:
+            with torch.no_grad():
+                vmax = np.float32(model.vp.detach().max().item())
+                grads = gradient_processor.forward(nz=model.nz, nx=model.nx, vmax=vmax, grad=grads, forw=forw)
+                model.vp.grad = grads.to(model.vp.dtype)
+        optimizer.step()
+        scheduler.step()
+        hist["loss"].append(loss_it)
+        hist["grad"].append(model.vp.grad.detach().clone())
+    return hist
