@@ -112,3 +112,36 @@ def acoustic_fwi(propagator, model, optimizer, scheduler, obs_p: torch.Tensor, i
         hist["loss"].append(loss_it)
         hist["grad"].append(model.vp.grad.detach().clone())
     return hist
+
+
+def elastic_fwi(propagator, model, optimizer, scheduler, obs: dict, iterations: int, batch_size: Optional[int] = None,
+                gradient_processor=None, waveform_normalize: bool = True, components: Sequence[str] = ("vx", "vz"),
+                parameters: Sequence[str] = ("vp", "vs", "rho"), fd_order: int = 4, misfit: Optional[Callable] = None,
+                checkpoint_segments: int = 1):
+    """The iteration loop of ``ElasticFWI.forward`` (ADFWI/fwi/elastic_fwi.py:196-320) for the particle-velocity components
+    (``inversion_component`` ``["vx", "vz"]``, for which the reference passes no illumination to the gradient processor,
+    :236,247), every step on the device.  ``obs[c]`` are the observed records (ns, nt, nr).  Returns
+    {"loss": [..], "grad": {parameter: [processed gradient per iteration]}}."""
+    misfit = misfit or (lambda syn, ob: l2_waveform_misfit(ob, syn, 1.0))
+    norm = (lambda r: r / torch.max(torch.abs(r), dim=1, keepdim=True).values) if waveform_normalize else (lambda r: r)
+    ob = {c: norm(obs[c]) for c in components}
+    hist = {"loss": [], "grad": {k: [] for k in parameters}}
+    for _ in range(iterations):
+        optimizer.zero_grad()
+        loss_it = 0.0
+        for pos in shot_batches(propagator.src_n, batch_size):
+            rec = propagator.forward(shot_index=pos, fd_order=fd_order, checkpoint_segments=checkpoint_segments)
+            loss = sum(misfit(norm(rec[c]), ob[c][pos]) for c in components)
+            loss.backward()
+            loss_it += float(loss.item())
+        for k in parameters:
+            p = getattr(model, k)
+            if gradient_processor is not None and p.grad is not None:
+                with torch.no_grad():
+                    vmax = np.float32(p.detach().max().item())
+                    p.grad = gradient_processor.forward(nz=model.nz, nx=model.nx, vmax=vmax, grad=p.grad, forw=None).to(p.dtype)
+            hist["grad"][k].append(p.grad.detach().clone())
+        optimizer.step()
+        scheduler.step()
+        hist["loss"].append(loss_it)
+    return hist
