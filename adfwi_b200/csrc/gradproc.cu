@@ -14,6 +14,7 @@ namespace adfwi {
 namespace {
 
 constexpr int GP_MAX_SPAN = 512;
+constexpr int GP_MAX_BLOCKS = 256;          // partial maxima of the two-stage reductions
 
 struct GPlan { double *g, *t0, *t1, *f, *wz, *wx, *scal; size_t bytes; };
 
@@ -25,7 +26,7 @@ GPlan gp_plan(int nz, int nx, void* ws)
     P.g = cv.take<double>(n); P.t0 = cv.take<double>(n); P.t1 = cv.take<double>(n);
     P.f = cv.take<double>(2 * GP_MAX_SPAN + 1);
     P.wz = cv.take<double>(nz); P.wx = cv.take<double>(nx);
-    P.scal = cv.take<double>(8);
+    P.scal = cv.take<double>(8 + GP_MAX_BLOCKS);
     P.bytes = cv.off;
     return P;
 }
@@ -74,12 +75,12 @@ __global__ void gp_conv_cols(int nz, int nx, int span, const double* __restrict_
     for (int k = k0; k <= k1; ++k) acc += f[k] * in[(size_t)(z + k - span) * nx + x];
     out[(size_t)z * nx + x] = acc / (wz[z] * wx[x]);
 }
-// mode 0: max(v), 1: max(|v|), 2: max(v + 1e-5)   (one block; planes are a few MB)
+// two-stage maximum.  mode 0: max(v), 1: max(|v|), 2: max(v + 1e-5), 3: max of the partial results
 __global__ void gp_max(size_t n, int mode, const double* __restrict__ v, double* __restrict__ res)
 {
-    __shared__ double sh[1024];
+    __shared__ double sh[256];
     double m = -INFINITY;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double a = v[i];
         a = mode == 1 ? fabs(a) : (mode == 2 ? a + 1e-5 : a);
         m = fmax(m, a);
@@ -90,7 +91,7 @@ __global__ void gp_max(size_t n, int mode, const double* __restrict__ v, double*
         if ((int)threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) *res = sh[0];
+    if (threadIdx.x == 0) res[blockIdx.x] = sh[0];
 }
 __global__ void gp_load_f32(size_t n, const float* __restrict__ in, double* __restrict__ out)
 {
@@ -162,6 +163,19 @@ __global__ void gp_norm(size_t n, int is32, double vmax, const double* __restric
 
 inline unsigned nb(size_t n) { return (unsigned)((n + 255) / 256); }
 
+// res[0] = maximum over v[0..n) in the given mode (partials parked behind the scalars of the plan)
+int gp_reduce_max(const GPlan& P, cudaStream_t st, size_t n, int mode, const double* v, double* res)
+{
+    unsigned blocks = nb(n);
+    if (blocks > (unsigned)GP_MAX_BLOCKS) blocks = GP_MAX_BLOCKS;
+    double* part = P.scal + 8;
+    gp_max<<<blocks, 256, 0, st>>>(n, mode, v, part);
+    ADFWI_LAUNCH_CHECK();
+    gp_max<<<1, 256, 0, st>>>(blocks, 3, part, res);
+    ADFWI_LAUNCH_CHECK();
+    return ADFWI_OK;
+}
+
 // smooth2d (:30-49) of the nz x nx plane `in` -> `out` (may alias `in`); tmp is a scratch plane
 int gp_smooth(const GPlan& P, cudaStream_t st, int nz, int nx, int span, const double* in, double* out, double* tmp)
 {
@@ -225,8 +239,8 @@ extern "C" int adfwi_gradproc_forward(const adfwi_gradproc_desc* d, const float*
             ADFWI_LAUNCH_CHECK();
             int rc = gp_smooth(P, st, nz, nx, d->grad_mute / 2, P.t1, P.t1, P.t0);
             if (rc) return rc;
-            gp_max<<<1, 1024, 0, st>>>(n, 0, P.t1, P.scal);
-            ADFWI_LAUNCH_CHECK();
+            rc = gp_reduce_max(P, st, n, 0, P.t1, P.scal);
+            if (rc) return rc;
             gp_taper_land_finish<<<nb(n), 256, 0, st>>>(n, d->thred, P.scal, P.t1);
             ADFWI_LAUNCH_CHECK();
         }
@@ -242,8 +256,8 @@ extern "C" int adfwi_gradproc_forward(const adfwi_gradproc_desc* d, const float*
         ADFWI_LAUNCH_CHECK();
         int rc = gp_smooth(P, st, nz, nx, d->illum_span, P.t1, P.t1, P.t0);
         if (rc) return rc;
-        gp_max<<<1, 1024, 0, st>>>(n, 2, P.t1, P.scal + 1);
-        ADFWI_LAUNCH_CHECK();
+        rc = gp_reduce_max(P, st, n, 2, P.t1, P.scal + 1);
+        if (rc) return rc;
         gp_precond<<<nb(n), 256, 0, st>>>(n, P.t1, P.scal + 1, P.g);
         ADFWI_LAUNCH_CHECK();
         is32 = 0;
@@ -264,8 +278,8 @@ extern "C" int adfwi_gradproc_forward(const adfwi_gradproc_desc* d, const float*
         }
     }
     if (d->norm_grad) {                                                   // :134-135
-        gp_max<<<1, 1024, 0, st>>>(n, 1, P.g, P.scal + 2);
-        ADFWI_LAUNCH_CHECK();
+        int rc = gp_reduce_max(P, st, n, 1, P.g, P.scal + 2);
+        if (rc) return rc;
         gp_norm<<<nb(n), 256, 0, st>>>(n, is32, d->vmax, P.scal + 2, P.g, out);
         ADFWI_LAUNCH_CHECK();
     } else {
