@@ -5,26 +5,29 @@
 // the generic kernels of elastic.cu (-fmad=false): forward records stay bit-identical to the CPU
 // reference.  Used for abc_type "PML"; the sponge (ABL) variants run the generic kernels.
 //
-// Two launches per forward step and two per reverse step, each a single stencil layer deep:
+// Default: ONE launch per forward step (elf_f) and ONE per reverse step (elf_b, O(2,4)); each fuses two dependent stencil
+// layers by recomputing the first layer on a ring around the tile, so the intermediate sums / cotangents never travel to
+// HBM (see the banners of elf_f and elf_b).  The single-layer kernels below remain as switchable fallbacks and as the
+// O(2,6) reverse step:
 //   elf_s  : stress update.  Reads the 4 velocity split fields with a halo (sums and the free-surface
 //            velocity rows are formed on chip), updates the 6 stress split fields IN PLACE (own cell
 //            only), writes the 3 stress sums and, in recording mode, the 4 velocity derivatives the
 //            adjoint needs (history; own cell, so the adjoint needs no halo and no recomputation).
 //   elf_v  : velocity update.  Reads the 3 stress sums with a halo (free-surface mirrors applied on
 //            chip), updates the 4 velocity split fields in place, samples the receivers, writes the 4
-//            stress derivatives of the history.
+//            stress derivatives of the history.                      (ADFWI_B200_EL_SPLIT=1: elf_s + elf_v)
 //   elf_k1 : adjoint of the velocity update: record cotangents + free-surface transpose on chip,
 //            own-cell transpose on tile + ring (halo recompute), gather of the operator transposes
 //            into the stress-sum cotangents; g_bx, g_bz accumulate in registers.
 //   elf_k2 : adjoint of the stress update: same structure; g_C11, g_C13, g_C33, g_C55 in registers,
-//            gather into the velocity-sum cotangents; g_src.
-// Common skeleton (the one of acoustic_fused.cu): a CTA of 128 threads owns one 64(x) x 16(z) tile
-// and walks through a chunk of the launch's shots.  Coefficients, PML factors and gradient sums of
-// the thread's 8 cells stay in REGISTERS for the whole walk; per shot every field a kernel touches
-// is brought into shared memory by TMA (hardware zero fill outside the grid) into a double buffer,
-// the loads of shot s+1 in flight while shot s is computed; all shared-memory traffic is 128-bit.
-// Tiles whose neighbourhood has no damping run a variant without the PML factors (x*1 == x exactly).
-// Launches are chained with programmatic dependent launch.
+//            gather into the velocity-sum cotangents; g_src.        (ADFWI_B200_EL_ADJ_SPLIT=1 or O(2,6): elf_k1 + elf_k2)
+// Common skeleton (the one of acoustic_fused.cu): a CTA of 256 threads owns one 64(x) x 16(z) tile (one float4 of 4
+// x-cells per thread) and walks through a chunk of the launch's shots.  Coefficients, PML factors and gradient sums of
+// the thread's cells stay in REGISTERS for the whole walk; per shot every field a kernel touches is brought into shared
+// memory by TMA (hardware zero fill outside the grid), the loads of the next shot in flight while this one is computed;
+// all shared-memory traffic is 128-bit.  Tiles whose neighbourhood has no damping run a variant without the PML factors
+// (x*1 == x exactly) and, in the adjoint, stage only one half of each split pair (elf_tile_class).  (tile, chunk) items
+// beyond a CTA's first are drawn from a per-launch atomic counter.  Launches are chained with programmatic dependent launch.
 #include "common.cuh"
 #ifndef ADFWI_HOST_EMUL
 #include "tma.cuh"
