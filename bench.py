@@ -422,11 +422,11 @@ def run_b200_elastic(args, wl):
     grads = ("eps", "delta") if wl.get("vti") else ("vp", "vs", "rho")
     survey = syn.surface_survey(nx, ns_total, wl["nr"], nt, dt, wl["f0"], src_z=wl["z_sr"], rcv_z=wl["z_sr"])
     mk = lambda vp, req: syn.ElasticGridModel(vp, mk_vs(vp), mk_rho(vp), eps=eps, delta=delta, dx=dx, dz=dx, nabc=nabc,
-                                              free_surface=True, abc_type="PML", requires_grad=req, device=dev)
+                                              free_surface=True, abc_type=args.abc, requires_grad=req, device=dev)
     true_model, model = mk(vp_true, ()), mk(vp_init, grads)
     prop_true = ElasticPropagator(true_model, survey, device=dev)
     prop = ElasticPropagator(model, survey, device=dev)
-    prop.bcx, prop.bcz = prop_true.bcx, prop_true.bcz
+    prop.bcx, prop.bcz, prop.damp = prop_true.bcx, prop_true.bcz, prop_true.damp
     shots = np.arange(lo, hi)
     params = [getattr(model, k) for k in grads]
 
@@ -514,13 +514,19 @@ def run_b200_elastic(args, wl):
         peak, peak_src = measured_peak_gbs()
         avg = {k: v[0] / v[1] for k, v in kt.items()}
         roof = None
-        adj = avg.get("el_adj_vel", 0.0) + avg.get("el_adj_stress", 0.0) + avg.get("el_adj_fused", 0.0)
-        fwd = avg.get("el_fwd_stress", 0.0) + avg.get("el_fwd_vel", 0.0) + avg.get("el_fwd_fused", 0.0)
+        adj = avg.get("el_adj_vel", 0.0) + avg.get("el_adj_stress", 0.0) + avg.get("el_adj_fused", 0.0) + avg.get("el_adj_inject", 0.0)
+        fwd = avg.get("el_fwd_stress", 0.0) + avg.get("el_fwd_vel", 0.0) + avg.get("el_fwd_fused", 0.0) + avg.get("el_record", 0.0)
+        if args.abc != "PML":       # sponge (ABL): 5 unsplit fields, SURVEY.md 8(d): forward 64 B (+20 B recording), adjoint 84 B
+            B_fwd, B_adj = 84.0, 84.0
+        else:
+            B_fwd, B_adj = B_EL_FWD_SAVE, B_EL_ADJ
         adj_name = "adjoint step (elf_b)" if "el_adj_fused" in avg else "adjoint step (elf_k1 + elf_k2)"
         fwd_name = "forward step, recording (elf_f)" if "el_fwd_fused" in avg else "forward step, recording (elf_s + elf_v)"
         cells = batch * nzp * nxp            # one launch advances every shot of the batch by one step
         if adj > 0 and fwd > 0:
-            dom_name, dom_ms, dom_bytes = ((adj_name, adj, B_EL_ADJ) if adj >= fwd else (fwd_name, fwd, B_EL_FWD_SAVE))
+            if args.abc != "PML":
+                adj_name, fwd_name = "adjoint step (generic ABL kernels)", "forward step, recording (generic ABL kernels)"
+            dom_name, dom_ms, dom_bytes = ((adj_name, adj, B_adj) if adj >= fwd else (fwd_name, fwd, B_fwd))
             ach = dom_bytes * cells / (dom_ms * 1e-3) / 1e9
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -536,20 +542,28 @@ def run_b200_elastic(args, wl):
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "kernel": dom_name, "avg_launch_ms": dom_ms, "algorithmic_bytes_per_cell_update": dom_bytes,
                     "cells_per_launch": cells, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
-                    "whole_step_frac": B_EL_GRAD_STEP / 2 * value * 1e9 / world / (peak * 1e9),
+                    "whole_step_frac": (B_fwd + B_adj) / 2 * value * 1e9 / world / (peak * 1e9),
                     "note": "forward and reverse step are one launch each (elf_f, elf_b); the timed region also holds the recomputation "
                             "sweep of the checkpointed segments, which is overhead, not counted work",
-                    "frac_by_sweep": {"forward_recording": B_EL_FWD_SAVE * cells / (fwd * 1e-3) / 1e9 / peak,
-                                      "adjoint": B_EL_ADJ * cells / (adj * 1e-3) / 1e9 / peak},
+                    "frac_by_sweep": {"forward_recording": B_fwd * cells / (fwd * 1e-3) / 1e9 / peak,
+                                      "adjoint": B_adj * cells / (adj * 1e-3) / 1e9 / peak},
                     "per_kernel_avg_ms": avg}
         cns, cnt = cpu_sample_size()
         cpu_v, cpu_s = cpu_gradient_sample(wl, cns, cnt)
+        if roof is not None and args.abc != "PML":
+            # the generic kernels advance the library's own shot groups, not the whole batch, per launch: only the
+            # whole-gradient fraction is meaningful here
+            w = roof["whole_step_frac"]
+            roof.update({"kernel": "whole gradient (generic ABL kernels: stress, velocity, record + their adjoints)", "frac": w,
+                         "achieved": w * peak, "frac_by_sweep": None, "avg_launch_ms": None, "cells_per_launch": None, "traffic": None,
+                         "algorithmic_bytes_per_cell_update": (B_fwd + B_adj) / 2,
+                         "note": "sponge (ABL) boundary: 5 unsplit fields, forward 84 B (64 + 20 recording), adjoint 84 B per cell-update"})
         line = {
             "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "shots_per_gpu": ns_local, "shots_total": ns_total,
-                       "batch_size": batch, "padded_grid": [nzp, nxp], "nt": nt, "receivers": wl["nr"], "gradients": list(grads),
+                       "batch_size": batch, "padded_grid": [nzp, nxp], "nt": nt, "receivers": wl["nr"], "gradients": list(grads), "abc_type": args.abc,
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2; no explicit flush)",
                        "parallelism": f"shots sharded over {world} GPU(s), one all-reduce of the gradients"},
             "shots_per_s": ns_total * args.steps / (ms * 1e-3),
@@ -579,6 +593,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--shots", type=int, default=0, help="shots per GPU (default: the workload's share of an 8-GPU job)")
     ap.add_argument("--batch", type=int, default=0, help="shots per propagator call (default: the workload's)")
+    ap.add_argument("--abc", default="PML", choices=["PML", "gerjan"], help="elastic workloads: split PML (fused kernels) or Cerjan sponge (ABL, generic kernels)")
     ap.add_argument("--nt", type=int, default=0, help="time steps (default: the workload's; shorter = a slice, labelled in config.nt)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
