@@ -231,10 +231,12 @@ def run_b200(args, wl):
     lib = _lib.load()
 
     nz, nx, nabc, nt, dt, dx = wl["nz"], wl["nx"], wl["nabc"], wl["nt"], wl["dt"], wl["dx"]
-    ns_local = max(wl["shots8"] // 8, 1)
+    if args.nt:
+        nt = args.nt
+    ns_local = args.shots or max(wl["shots8"] // 8, 1)
     ns_total = ns_local * world
     lo, hi = D.shard_shots(ns_total, rank, world)
-    batch = min(wl["batch"], ns_local)
+    batch = min(args.batch or wl["batch"], ns_local)
     nzp, nxp = nz + 2 * nabc, nx + 2 * nabc
 
     vp_true = syn.marmousi_like_vp(nz, nx)
@@ -350,8 +352,9 @@ def run_b200(args, wl):
             if os.path.exists(tpath):
                 try:
                     tj = json.load(open(tpath))
-                    if tj.get("workload") == args.workload and tj.get("batch") == batch:
-                        traffic = tj.get(dom_key)
+                    ent = tj.get(args.workload) if isinstance(tj.get(args.workload), dict) else (tj if tj.get("workload") == args.workload else None)
+                    if ent and ent.get("batch") == batch:
+                        traffic = ent.get(dom_key)
                 except Exception:
                     traffic = None
             if dom_ms > 0:
