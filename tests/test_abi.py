@@ -37,10 +37,28 @@ def test_library_builds_loads_and_exports_all_symbols():
     assert lib.adfwi_elastic_workspace_bytes(ctypes.byref(e)) == 0
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every descriptor as gcc lays the header out == the ctypes mirrors of adfwi_b200/_lib.py."""
+    import subprocess
     from adfwi_b200 import _lib
     assert ctypes.sizeof(_lib.AcousticDesc) == 4 * 19
     assert ctypes.sizeof(_lib.ElasticDesc) == 4 * 28
+    mirrors = {"adfwi_acoustic_desc": _lib.AcousticDesc, "adfwi_elastic_desc": _lib.ElasticDesc, "adfwi_gradproc_desc": _lib.GradProcDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "adfwi_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_no_cpu_fallback():
