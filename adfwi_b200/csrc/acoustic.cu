@@ -435,6 +435,7 @@ static bool ac_use_fused(const adfwi_acoustic_desc* d)
 #ifdef ADFWI_HOST_EMUL
     (void)d; return false;
 #else
+    if (d->nzp >= 32768 || d->nxp >= 65536) return false;      // the fused path packs receiver cells as (z<<16)|x
     return !(d->save_history && d->need_g_alpha2) && !(d->reserved[0] & 1);
 #endif
 }

@@ -789,10 +789,15 @@ static_assert(FWD_STAGES <= 4 && ADJ_STAGES <= 4, "four mbarrier slots are reser
 static_assert(2 * (FWD_SMEM + 1024) <= 233472 && 2 * (ADJ_SMEM + 1024) <= 233472, "two CTAs per SM must fit in shared memory");
 constexpr int CTAS_PER_SM = 2;
 
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
 int acf_num_sms()
 {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    static int cache[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    int n = cache[dev];
+    if (!n) { cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; cache[dev] = n; }
     return n;
 }
 
@@ -978,9 +983,14 @@ int acf_forward_step(const FPlan& P, const StepMaps& M, cudaStream_t st, int cur
     return ADFWI_OK;
 }
 
+// function attributes are per device: the >48 KB dynamic shared-memory opt-in is made once per device ordinal
 int acf_init_kernels()
 {
-    static bool done = false;
+    static bool done_dev[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    bool& done = done_dev[dev];
     if (done) return 0;
     int rc = 0;
     rc |= acf_set_smem(ac_fwd_fused<true, true, true>, FWD_SMEM);   rc |= acf_set_smem(ac_fwd_fused<true, true, false>, FWD_SMEM);
@@ -1015,7 +1025,7 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
     FPlan P;
     acf_make_plan(d, ws, &P, 148);
     const FGeom& g = P.g;
-    if (g.nzp >= 32768 || g.nxp >= 65536) return ADFWI_E_DIMS;      // receiver cells are packed as (z<<16)|x
+    if (g.nzp >= 32768 || g.nxp >= 65536) return ADFWI_E_DIMS;      // unreachable: ac_use_fused() sends such grids to the generic kernels
     int rc = acf_init_kernels();
     if (rc) return rc;
     StepMaps M;

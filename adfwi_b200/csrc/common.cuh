@@ -20,6 +20,8 @@ namespace adfwi {
 
 extern std::atomic<uint64_t> g_launches;   // diagnostic counter behind adfwi_launch_count()
 
+constexpr int kMaxDevices = 64;            // per-device caches (SM count, kernel attributes) are indexed by device ordinal
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

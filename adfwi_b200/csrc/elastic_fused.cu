@@ -2171,10 +2171,15 @@ __global__ void elf_illum_out(int n, const float* __restrict__ ill, float* o0, f
 // ---- host side -------------------------------------------------------------------------------------
 constexpr int CTAS_PER_SM = 2;
 
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
 int elf_num_sms()
 {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    static int cache[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    int n = cache[dev];
+    if (!n) { cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; cache[dev] = n; }
     return n;
 }
 
@@ -2337,9 +2342,14 @@ static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <=
               2 * (b_smem<2>() + 1024) <= 233472,
               "two CTAs per SM must fit in shared memory (the O(2,6) fused forward kernel runs one CTA per SM)");
 
+// function attributes are per device: the >48 KB dynamic shared-memory opt-in is made once per device ordinal
 template <int NN> int elf_init_kernels()
 {
-    static bool done = false;
+    static bool done_dev[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    bool& done = done_dev[dev];
     if (done) return 0;
     int rc = 0;
     rc |= elf_set_smem(elf_s<NN, true, true>, s_smem<NN>());   rc |= elf_set_smem(elf_s<NN, true, false>, s_smem<NN>());

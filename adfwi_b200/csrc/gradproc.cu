@@ -75,6 +75,9 @@ __global__ void gp_conv_cols(int nz, int nx, int span, const double* __restrict_
     for (int k = k0; k <= k1; ++k) acc += f[k] * in[(size_t)(z + k - span) * nx + x];
     out[(size_t)z * nx + x] = acc / (wz[z] * wx[x]);
 }
+// numpy's max() propagates NaN (a diverged simulation must stay visible: the reference then returns an all-NaN
+// gradient); fmax() would drop it
+__device__ __forceinline__ double nanmax(double m, double a) { return (a != a || m != m) ? NAN : fmax(m, a); }
 // two-stage maximum.  mode 0: max(v), 1: max(|v|), 2: max(v + 1e-5), 3: max of the partial results
 __global__ void gp_max(size_t n, int mode, const double* __restrict__ v, double* __restrict__ res)
 {
@@ -83,12 +86,12 @@ __global__ void gp_max(size_t n, int mode, const double* __restrict__ v, double*
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double a = v[i];
         a = mode == 1 ? fabs(a) : (mode == 2 ? a + 1e-5 : a);
-        m = fmax(m, a);
+        m = nanmax(m, a);
     }
     sh[threadIdx.x] = m;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = nanmax(sh[threadIdx.x], sh[threadIdx.x + s]);
         __syncthreads();
     }
     if (threadIdx.x == 0) res[blockIdx.x] = sh[0];

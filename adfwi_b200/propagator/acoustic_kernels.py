@@ -139,6 +139,7 @@ class AcousticFD(torch.autograd.Function):
         desc, ws = ctx.desc, ctx.ws
         if ws is None:
             raise RuntimeError("adfwi_b200: backward called but no history was saved")
+        _DeferredChecks.poll()      # input checks of the forward call that have completed since
         dev = planes[0].device
         need = ctx.need
         with torch.cuda.device(dev):
@@ -181,9 +182,60 @@ def coefficient_planes(v, rho, damp, dt, dz, nabc, free_surface):
     return alpha1, alpha2, kappa1, kappa2, kappa3
 
 
-def _check_indices(name, idx, hi):
-    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= hi):
-        raise IndexError(f"adfwi_b200: {name} out of range for a grid of {hi} points")
+class _DeferredChecks:
+    """Input validation without a host-device synchronisation per call.
+
+    The range test of the source / receiver indices (and the zero test of the TTI moduli in the elastic
+    shim) is evaluated ON THE DEVICE; the resulting flags travel to pinned host memory with a
+    non-blocking copy and are read once their event has completed -- at the start of the next
+    ``forward_kernel`` call, in ``backward`` or through :func:`flush_checks`.  A bad input therefore
+    raises one call late, but it still raises (the kernels themselves skip out-of-grid cells, so
+    nothing is read or written out of bounds in the meantime).  ``ADFWI_B200_SYNC_CHECKS=1`` makes
+    every check blocking."""
+    pending = []
+    blocking = os.environ.get("ADFWI_B200_SYNC_CHECKS", "0") == "1"
+
+    @classmethod
+    def submit(cls, flags, messages, exc=IndexError):
+        host = torch.empty(flags.shape, dtype=flags.dtype, pin_memory=True)
+        host.copy_(flags, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(flags.device))
+        cls.pending.append((ev, host, messages, exc))
+        cls.poll(block=cls.blocking)
+
+    @classmethod
+    def poll(cls, block=False):
+        keep, pend = [], cls.pending
+        cls.pending = []
+        err = None
+        for item in pend:
+            ev, host, messages, exc = item
+            if block:
+                ev.synchronize()
+            if not ev.query():
+                keep.append(item)
+                continue
+            bad = [m for m, f in zip(messages, host.tolist()) if f]
+            if bad and err is None:
+                err = exc("adfwi_b200: " + "; ".join(bad))
+        cls.pending = keep + cls.pending
+        if err is not None:
+            raise err
+
+
+def flush_checks():
+    """Block until every deferred input check has been evaluated; raises if one failed."""
+    _DeferredChecks.poll(block=True)
+
+
+def _check_indices(pairs):
+    """pairs: [(name, index tensor on the device, exclusive upper bound)]; see :class:`_DeferredChecks`."""
+    pairs = [(n, t, hi) for n, t, hi in pairs if t.numel()]
+    if not pairs:
+        return
+    flags = torch.stack([(t.min() < 0) | (t.max() >= hi) for _, t, hi in pairs])
+    _DeferredChecks.submit(flags, [f"{n} out of range for a grid of {hi} points" for n, _, hi in pairs])
 
 
 def forward_kernel(nx: int, nz: int, dx: float, dz: float, nt: int, dt: float,
@@ -213,8 +265,8 @@ def forward_kernel(nx: int, nz: int, dx: float, dz: float, nt: int, dt: float,
     dev = v.device
     src_x, src_z = src_x.to(dev), src_z.to(dev)
     rcv_x, rcv_z = rcv_x.to(dev), rcv_z.to(dev)
-    _check_indices("src_x", src_x, nx); _check_indices("src_z", src_z, nz)
-    _check_indices("rcv_x", rcv_x, nx); _check_indices("rcv_z", rcv_z, nz)
+    _DeferredChecks.poll()
+    _check_indices([("src_x", src_x, nx), ("src_z", src_z, nz), ("rcv_x", rcv_x, nx), ("rcv_z", rcv_z, nz)])
     alpha1, alpha2, kappa1, kappa2, kappa3 = coefficient_planes(v, rho, damp.to(dev).float(), dt, dz, nabc, free_surface)
     rcv_p, rcv_u, rcv_w, ill_p, ill_u, ill_w = AcousticFD.apply(
         alpha1, alpha2, kappa1, kappa2, kappa3, src_v.to(dev),

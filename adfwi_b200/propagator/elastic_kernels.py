@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib
-from .acoustic_kernels import _check_indices, _ptr, _require_cuda, config
+from .acoustic_kernels import _DeferredChecks, _check_indices, _ptr, _require_cuda, config
 
 # fp32 bit patterns of DiffCoef(NN,'s') = inv(A)@B evaluated in fp32 (elastic_kernels.py:20-58):
 # O(2,4) 9/8, -1/24; O(2,6) 75/64, -25/384 (one ulp off the nearest float -- an artefact of the
@@ -126,6 +126,7 @@ class ElasticFD(torch.autograd.Function):
         desc, ws = ctx.desc, ctx.ws
         if ws is None:
             raise RuntimeError("adfwi_b200: backward called but no history was saved")
+        _DeferredChecks.poll()      # input checks of the forward call that have completed since
         dev = planes[0].device
         need = ctx.need
         with torch.cuda.device(dev):
@@ -190,9 +191,12 @@ def forward_kernel(nx: int, nz: int, dx: float, dz: float, nt: int, dt: float,
     pml = abc_type.lower() in ["pml"]
     C11, C13, C15, C33, C35, C55 = CC[0], CC[2], CC[4], CC[11], CC[13], CC[18]
     _require_cuda(C11, C13, C33, C55, bx, bz, src_v)
-    for name, t in (("C15", C15), ("C35", C35)):
-        if t is not None and torch.is_tensor(t) and bool((t != 0).any()):
-            raise NotImplementedError(f"adfwi_b200: non-zero {name} (TTI) is not supported; the reference never builds it")
+    _DeferredChecks.poll()
+    tti = [(name, t) for name, t in (("C15", C15), ("C35", C35)) if t is not None and torch.is_tensor(t) and t.is_cuda]
+    if tti:       # evaluated on the device, reported without a synchronisation (see _DeferredChecks)
+        _DeferredChecks.submit(torch.stack([(t != 0).any() for _, t in tti]),
+                               [f"non-zero {name} (TTI) is not supported; the reference never builds it" for name, _ in tti],
+                               exc=NotImplementedError)
     if src_v.dim() != 2 or src_v.shape[0] != src_n or src_v.shape[1] != nt:
         raise ValueError("adfwi_b200: src_v must be (src_n, nt)")
     dev = C11.device
@@ -210,10 +214,16 @@ def forward_kernel(nx: int, nz: int, dx: float, dz: float, nt: int, dt: float,
             raise ValueError("adfwi_b200: sponge boundary needs damp")
         bc1, bc2 = full_plane(damp.to(dev), nzp, nxp, 0, NN, free_surface), None
     src_x, src_z, rcv_x, rcv_z = (t.to(dev) for t in (src_x, src_z, rcv_x, rcv_z))
-    _check_indices("src_x", src_x, nx); _check_indices("src_z", src_z, nz)
-    _check_indices("rcv_x", rcv_x, nx); _check_indices("rcv_z", rcv_z, nz)
+    _check_indices([("src_x", src_x, nx), ("src_z", src_z, nz), ("rcv_x", rcv_x, nx), ("rcv_z", rcv_z, nz)])
+    # the kernels index the moment tensors as mt[s*9 + ...]: (src_n,3,3) is required; a single (3,3) tensor (which the
+    # reference's step functions accept for one wavelet) is broadcast
+    MT = MT.to(dev).float()
+    if MT.dim() == 2 and tuple(MT.shape) == (3, 3):
+        MT = MT.expand(src_n, 3, 3)
+    if tuple(MT.shape) != (src_n, 3, 3):
+        raise ValueError(f"adfwi_b200: MT must have shape ({src_n},3,3) (one moment tensor per selected shot), got {tuple(MT.shape)}")
     zoff = NN if free_surface else NN + nabc
-    out = ElasticFD.apply(*planes, src_v.to(dev), bc1, bc2, MT.to(dev).float(),
+    out = ElasticFD.apply(*planes, src_v.to(dev), bc1, bc2, MT,
                           src_x + nabc, src_z + zoff, rcv_x + nabc, rcv_z + zoff,
                           int(nz), int(nx), int(nabc), bool(free_surface), int(fd_order), bool(pml),
                           float(dt), float(dx), float(dz), int(n_segments))

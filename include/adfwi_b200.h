@@ -12,8 +12,11 @@
  *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
  *   - all arrays are dense row-major fp32 (indices int64), [z][x] with x fastest;
  *   - the caller owns every buffer including the workspace; the library never allocates or
- *     frees device memory and keeps no global state; all work is enqueued on `stream`
- *     (a cudaStream_t passed as void*), no implicit synchronisation;
+ *     frees device memory; all work is enqueued on `stream` (a cudaStream_t passed as void*), no
+ *     implicit synchronisation.  Process-wide state is limited to diagnostics and caches that do not
+ *     change results: the launch counter, the optional sampled kernel timing (adfwi_timing_*),
+ *     per-device caches of the SM count / kernel attributes, and the A/B environment switches
+ *     ADFWI_B200_{PDL,EL_LEAN,EL_SPLIT,EL_ADJ_SPLIT} which are read once per process;
  *   - return value: 0 = ok, <0 = ADFWI_E_* (argument error, detected before any launch),
  *     >0 = cudaError_t of a failed launch.  adfwi_strerror() maps either to text.
  */

@@ -118,3 +118,51 @@ def test_fused_large_grid_matches_generic():
         for k in ("forward_wavefield_p", "forward_wavefield_u", "forward_wavefield_w"):
             assert rel_l2(out[False][0][k].cpu().numpy(), out[True][0][k].cpu().numpy()) < 1e-5
         assert rel_l2(out[False][1].cpu().numpy(), out[True][1].cpu().numpy()) < 1e-5, fs
+
+
+def test_out_of_range_indices_raise_without_a_per_call_sync(golden_dir):
+    """Index validation runs on the device and is reported without a host synchronisation per call
+    (acoustic_kernels._DeferredChecks): a bad receiver index raises at the latest at flush_checks()."""
+    from adfwi_b200.propagator import acoustic_kernels as ak
+    g = np.load(f"{golden_dir}/acoustic_fs.npz")
+    dev = torch.device("cuda:0")
+    t = lambda k: torch.tensor(g[k], device=dev)
+    ak.flush_checks()
+    bad_rx = t("rcv_x").clone(); bad_rx[0] = int(g["nx"])
+    with pytest.raises(IndexError, match="rcv_x"):
+        ak.forward_kernel(int(g["nx"]), int(g["nz"]), float(g["dx"]), float(g["dz"]), int(g["nt"]), float(g["dt"]), int(g["nabc"]),
+                          bool(g["free_surface"]), t("src_x"), t("src_z"), len(g["src_x"]), t("src_v"), bad_rx, t("rcv_z"),
+                          len(g["rcv_x"]), t("damp"), t("vp"), t("rho"), device=dev)
+        ak.flush_checks()
+    ak.flush_checks()     # nothing left pending
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process(golden_dir):
+    """Kernel attributes (the >48 KB dynamic shared-memory opt-in) are per device: forward + backward on cuda:1
+    after cuda:0 in one process."""
+    from adfwi_b200.propagator import acoustic_kernels as ak, elastic_kernels as ek
+    g = np.load(f"{golden_dir}/acoustic_fs.npz")
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        t = lambda k: torch.tensor(g[k], device=dev)
+        v = t("vp").requires_grad_(True)
+        rec = ak.forward_kernel(int(g["nx"]), int(g["nz"]), float(g["dx"]), float(g["dz"]), int(g["nt"]), float(g["dt"]), int(g["nabc"]),
+                                bool(g["free_surface"]), t("src_x"), t("src_z"), len(g["src_x"]), t("src_v"), t("rcv_x"), t("rcv_z"),
+                                len(g["rcv_x"]), t("damp"), v, t("rho"), device=dev)
+        (rec["p"] * t("W_p")).sum().backward()
+        assert np.array_equal(rec["p"].detach().cpu().numpy(), g["rec_p"]), dev
+        assert rel_l2(v.grad.cpu().numpy(), g["g_v_p"]) <= 2e-5, dev
+    ge = np.load(f"{golden_dir}/elastic_pml_o4_fs.npz")
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        t = lambda k: torch.tensor(ge[k], device=dev)
+        nz, nx = int(ge["nz"]), int(ge["nx"])
+        L = {k: t("in_" + k).requires_grad_(True) for k in ("C11", "C13", "C33", "C55", "bx", "bz")}
+        CC = [torch.zeros((nz, nx), device=dev)] * 21
+        CC[0], CC[2], CC[11], CC[18] = L["C11"], L["C13"], L["C33"], L["C55"]
+        rec = ek.forward_kernel(nx, nz, float(ge["dx"]), float(ge["dz"]), int(ge["nt"]), float(ge["dt"]), int(ge["nabc"]),
+                                bool(ge["free_surface"]), t("src_x"), t("src_z"), len(ge["src_x"]), t("src_v"), t("mt"), t("rcv_x"), t("rcv_z"),
+                                len(ge["rcv_x"]), "PML", t("bcx"), t("bcz"), None, None, None, L["bx"], L["bz"], CC, fd_order=4,
+                                n_segments=int(ge["segments"]), device=dev)
+        sum((rec[k] * t("W_" + k)).sum() for k in ("vx", "vz")).backward()
+        assert np.array_equal(rec["vz"].detach().cpu().numpy(), ge["rec_vz"]), dev
+        assert rel_l2(L["C11"].grad.cpu().numpy(), ge["g_C11_vel"]) <= 2e-5, dev

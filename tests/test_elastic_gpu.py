@@ -152,3 +152,26 @@ def test_kernel_variant_switches(golden_dir, switch):
                         "(test_golden_records_and_gradients and pml_o4 and cfg0) or (fused_large and shape1-4)"], env=env,
                        capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_moment_tensor_shape_is_validated(golden_dir):
+    """MT must be (src_n,3,3); a single (3,3) tensor is broadcast, anything else raises."""
+    from adfwi_b200.propagator import elastic_kernels as ek
+    g = np.load(f"{golden_dir}/elastic_pml_o4_fs.npz")
+    dev = torch.device("cuda:0")
+    t = lambda k: torch.tensor(g[k], device=dev)
+    nz, nx = int(g["nz"]), int(g["nx"])
+    CC = [torch.zeros((nz, nx), device=dev)] * 21
+    CC[0], CC[2], CC[11], CC[18] = t("in_C11"), t("in_C13"), t("in_C33"), t("in_C55")
+    ns = len(g["src_x"])
+    call = lambda mt: ek.forward_kernel(nx, nz, float(g["dx"]), float(g["dz"]), int(g["nt"]), float(g["dt"]), int(g["nabc"]),
+                                        bool(g["free_surface"]), t("src_x"), t("src_z"), ns, t("src_v"), mt, t("rcv_x"), t("rcv_z"),
+                                        len(g["rcv_x"]), "PML", t("bcx"), t("bcz"), None, None, None, t("in_bx"), t("in_bz"), CC,
+                                        fd_order=4, n_segments=1, device=dev)
+    with pytest.raises(ValueError, match="MT must have shape"):
+        call(t("mt")[: ns - 1])
+    one = t("mt")[0]
+    a = call(one)
+    b = call(one.expand(ns, 3, 3).contiguous())
+    for k in COMPS:
+        assert torch.equal(a[k], b[k]), k
