@@ -55,3 +55,66 @@ def test_boundary_profiles_match_reference(golden_dir):
         assert np.array_equal(bx, g["pmlx_" + tag]) and np.array_equal(bz, g["pmlz_" + tag])
         assert np.array_equal(bc.bc_gerjan(23, 17, 10.0, 10.0, pml=7, alpha=0.0053, free_surface=fs), g["gerjan_" + tag])
         assert np.array_equal(bc.bc_sincos(23, 17, 10.0, 10.0, pml=7, free_surface=fs), g["sincos_" + tag])
+
+
+def _l2_misfit_and_cotangent(rec, obs, dt):
+    """Misfit_waveform_L2 (fwi/misfit/L2.py:22-28) and d(loss)/d(rec) in numpy."""
+    r = obs.astype(np.float64) - rec.astype(np.float64)
+    n = np.sqrt(np.sum(r * r * dt, axis=1, keepdims=True))
+    return float(n.sum()), (-(r * dt) / np.where(n > 0, n, 1.0)).astype(np.float32)
+
+
+def test_acoustic_oracle_matches_reference_at_example_scale(golden_dir):
+    """The oracle against the UNMODIFIED reference at the acoustic example's own size and nt (148 x 260 padded, nt 1600,
+    4 shots; tests/golden/make_golden_scale.py): records bit-identical after 1600 steps, loss and vp gradient."""
+    g = np.load(f"{golden_dir}/acoustic_c1_scale.npz")
+    nabc, dt, dz = int(g["nabc"]), float(g["dt"]), float(g["dz"])
+    O.lib().oracle_set_threads(8)
+    coef = O.acoustic_coefficients(g["vp_init"], g["rho_init"], g["damp"], dt, dz, nabc, True)
+    cot = {}
+
+    def g_rcv(out):
+        cot["loss"], gp = _l2_misfit_and_cotangent(out["p"], g["obs_p"], dt)
+        return gp, None, None
+    out = O.acoustic_run(coef, nabc, True, dt, g["src_x"], g["src_z"], np.broadcast_to(g["wavelet"], (len(g["src_x"]), int(g["nt"]))).copy(),
+                         g["rcv_x"], g["rcv_z"], g_rcv=g_rcv, need_g_alpha2=False)
+    assert np.array_equal(out["p"], g["rec_p"])
+    assert np.array_equal(out["u"][:, :, ::5], g["rec_u"]) and np.array_equal(out["w"][:, :, ::5], g["rec_w"])
+    assert abs(cot["loss"] - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    gv, _ = O.acoustic_model_gradients(coef, out["g_alpha1"], None, dt, dz, nabc)
+    assert O.rel_l2(gv, g["g_vp"]) < 2e-5
+
+
+def test_elastic_oracle_matches_reference_at_example_scale(golden_dir):
+    """The oracle against the UNMODIFIED reference on the VTI example (132 x 280 padded, nt 1000, 2 shots, split-PML O(2,4),
+    AnisotropicElasticModel parameterisation): five records bit-identical after 1000 steps, loss, and the eps / delta / vp /
+    vs / rho gradients (oracle plane gradients chained through the torch restatement of the parameterisation)."""
+    import torch
+    from adfwi_b200 import synthetic as syn
+    g = np.load(f"{golden_dir}/vti_c4_scale.npz")
+    nz, nx, nabc, nt, dt, dx = int(g["nz"]), int(g["nx"]), int(g["nabc"]), int(g["nt"]), float(g["dt"]), float(g["dx"])
+    params = ("vp", "vs", "rho", "eps", "delta")
+    m = syn.ElasticGridModel(g["vp"], g["vs"], g["rho"], eps=g["eps_init"], delta=g["delta"], dx=dx, dz=dx, nabc=nabc, free_surface=True,
+                             abc_type="PML", requires_grad=params, device="cpu")
+    m.forward()
+    idx = {"C11": 0, "C13": 2, "C33": 11, "C55": 18}
+    outs = {k: (m.CC[idx[k]] if k in idx else getattr(m, k)) for k in PLANES}
+    planes = {k: v.detach().numpy() for k, v in outs.items()}
+    ns = len(g["src_x"])
+    O.lib().oracle_set_threads(8)
+    cot = {}
+
+    def g_rcv(out):
+        lx, gx = _l2_misfit_and_cotangent(out["vx"], g["obs_vx"], dt)
+        lz, gz = _l2_misfit_and_cotangent(out["vz"], g["obs_vz"], dt)
+        cot["loss"] = lx + lz
+        return None, None, None, gx, gz
+    out = O.elastic_run(planes, "PML", 4, True, nz, nx, nabc, dx, dx, dt, g["src_x"], g["src_z"], np.broadcast_to(g["wavelet"], (ns, nt)).copy(),
+                        np.broadcast_to(np.eye(3, dtype=np.float32), (ns, 3, 3)).copy(), g["rcv_x"], g["rcv_z"], bcx=g["bcx"], bcz=g["bcz"], g_rcv=g_rcv)
+    for k, s in (("vx", 1), ("vz", 1), ("txx", 6), ("tzz", 6), ("txz", 6)):
+        assert np.array_equal(out[k][:, :, ::s], g["rec_" + k]), f"record {k} differs from the reference bits"
+    assert abs(cot["loss"] - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    gm = torch.autograd.grad([outs[k] for k in PLANES], [getattr(m, k) for k in params],
+                             grad_outputs=[torch.tensor(out["g_own"][k], dtype=torch.float32) for k in PLANES])
+    for k, gr in zip(params, gm):
+        assert O.rel_l2(gr.numpy(), g["g_" + k]) < 5e-5, k
