@@ -184,28 +184,154 @@ def cpu_sample_size():
     return max(2, min(os.cpu_count() or 2, 16)), 50
 
 
+def cpu_port_warm(wl, reps=2):
+    """Warm mean of the oracle port on the bounded sample (first call discarded: page faults of the history, OpenMP start-up)."""
+    ns, nt = cpu_sample_size()
+    cpu_gradient_sample(wl, ns, nt)
+    vals, secs = zip(*[cpu_gradient_sample(wl, ns, nt) for _ in range(reps)])
+    return float(np.mean(vals)), float(np.mean(secs)), ns, nt
+
+
+def reference_objects(wl, ns, nt, device):
+    """The UNMODIFIED reference's own model / survey / propagator objects for an (ns shots x nt steps) sample of a
+    workload, on `device` ('cpu' or 'cuda:0').  Needs the reference package (oracle/ref_loader.py search path)."""
+    from oracle import ref_loader
+    from adfwi_b200 import synthetic as syn
+    ref_loader.load()
+    from ADFWI.survey import Source, Receiver, Survey
+    nz, nx, nabc, dx, dt, f0 = wl["nz"], wl["nx"], wl["nabc"], wl["dx"], wl["dt"], wl["f0"]
+    z = wl.get("z_sr", 1)
+    sx = np.round(np.linspace(2, nx - 3, ns)).astype(int) if ns > 1 else np.array([nx // 2])
+    rx = np.round(np.linspace(0, nx - 1, wl["nr"])).astype(int)
+    s = Source(nt=nt, dt=dt, f0=f0)
+    s.add_sources(src_x=sx, src_z=np.full(ns, z), src_wavelet=syn.integrated_ricker(nt, dt, f0 * 4).astype(np.float32), src_type="mt", src_mt=np.eye(3))
+    r = Receiver(nt=nt, dt=dt)
+    r.add_receivers(rcv_x=rx, rcv_z=np.full(len(rx), z), rcv_type="pr")
+    survey = Survey(source=s, receiver=r)
+    vp = syn.smooth2d(syn.marmousi_like_vp(nz, nx), 6)
+    if wl.get("kind") == "elastic":
+        from ADFWI.model import AnisotropicElasticModel, IsotropicElasticModel
+        from ADFWI.propagator import ElasticPropagator
+        vs, rho = (vp / np.sqrt(3.0)).astype(np.float32), syn.gardner_rho(vp)
+        if wl.get("vti"):
+            one = np.ones((nz, nx), np.float32)
+            model = AnisotropicElasticModel(0, 0, nx, nz, dx, dx, vp=vp, vs=vs, rho=rho, eps=0.1 * one, gamma=0 * one, delta=-0.1 * one,
+                                            eps_grad=True, delta_grad=True, free_surface=True, anisotropic_type="vti", abc_type="PML",
+                                            nabc=nabc, device=device)
+        else:
+            model = IsotropicElasticModel(0, 0, nx, nz, dx, dx, vp, vs, rho, vp_grad=True, vs_grad=True, rho_grad=True, free_surface=True,
+                                          abc_type="PML", nabc=nabc, auto_update_rho=False, auto_update_vp=False, device=device)
+        return model, ElasticPropagator(model, survey, device=device), ("vx", "vz")
+    from ADFWI.model import AcousticModel
+    from ADFWI.propagator import AcousticPropagator
+    model = AcousticModel(0, 0, nx, nz, dx, dx, vp, syn.gardner_rho(vp), vp_grad=True, free_surface=True, abc_type="PML", nabc=nabc, device=device)
+    return model, AcousticPropagator(model, survey, device=device), ("p",)
+
+
+def reference_gradient_sample(wl, ns, nt, device, reps, warmup):
+    """Time forward + L2 misfit + loss.backward() of the unmodified reference (its own autograd tape through the TorchScript time
+    loop, checkpoint_segments=4 as in its examples) on an ns x nt sample.  Returns (cell-updates/s, seconds per gradient)."""
+    import torch
+    from oracle import ref_loader
+    ref_loader.load()
+    from ADFWI.fwi.misfit import Misfit_waveform_L2
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1
+    model, prop, comps = reference_objects(wl, ns, nt, device)
+    fn = Misfit_waveform_L2(dt=wl["dt"])
+    elastic = wl.get("kind") == "elastic"
+    with torch.no_grad():
+        o = prop.forward()
+        obs = {c: 0.9 * o[c].detach() for c in comps}
+    secs = []
+    for i in range(warmup + reps):
+        for p in model.parameters():
+            p.grad = None
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rec = prop.forward(fd_order=4, checkpoint_segments=4) if elastic else prop.forward(checkpoint_segments=4)
+        loss = sum(fn.forward(obs[c], rec[c]) for c in comps)
+        loss.backward()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        if i >= warmup:
+            secs.append(time.perf_counter() - t0)
+    nzp = wl["nz"] + (wl["nabc"] + 2 if elastic else 2 * wl["nabc"])
+    cells = nzp * (wl["nx"] + 2 * wl["nabc"]) * ns * nt
+    sec = float(np.mean(secs))
+    return 2.0 * cells / sec, sec
+
+
+def cpu_baseline_entry(args, wl):
+    """`cpu_baseline` of the B200 arm: the unmodified reference on the host cores when its package is staged (kind "reference"),
+    else the C/OpenMP port (kind "port"); the port's warm mean is always reported beside it."""
+    from oracle import ref_loader
+    cores = os.cpu_count()
+    port_v, port_s, pns, pnt = cpu_port_warm(wl, reps=2)
+    port = {"value": port_v / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/ C port (OpenMP, all host threads), {pns} shots x {pnt} steps of the {args.workload} grid, forward+adjoint, "
+                      f"warm mean of 2, {port_s:.1f} s each"}
+    if ref_loader.available():
+        elastic = wl.get("kind") == "elastic"
+        ns, nt = (2, 20) if elastic else (2, 100)
+        try:
+            val, sec = reference_gradient_sample(wl, ns, nt, "cpu", reps=1, warmup=1)
+            return {"value": val / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "reference",
+                    "sample": f"unmodified reference (propagator.forward + Misfit_waveform_L2 + loss.backward(), checkpoint_segments=4, device='cpu', "
+                              f"torch {cores} threads), {ns} shots x {nt} steps of the {args.workload} grid, {sec:.1f} s per gradient after one warm-up",
+                    "port": port}
+        except Exception as e:
+            port["sample"] += f" (reference failed: {type(e).__name__}: {e})"
+    return port
+
+
 def run_reference(args, wl):
+    """Reference arm: the UNMODIFIED reference (pure PyTorch: TorchScript time loop + autograd tape) on the host cores when its
+    package is present (baseline/_ref staged by baseline/stage_reference.py, or /root/reference), timed on a bounded sample of the
+    workload; otherwise the C/OpenMP port under oracle/.  The port's number and -- when a GPU is visible -- the reference's own
+    CUDA path (device='cuda', the mode all its examples run in) are reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ns, nt = cpu_sample_size()
-    vals, secs = [], []
-    for i in range(args.warmup + args.steps):
-        v, s = cpu_gradient_sample(wl, ns, nt)
-        if i >= args.warmup:
-            vals.append(v); secs.append(s)
-    val = float(np.mean(vals)) / 1e9
+    from oracle import ref_loader
     cores = os.cpu_count()
+    port_v, port_s, pns, pnt = cpu_port_warm(wl, reps=max(args.steps, 1))
+    port = {"value": port_v / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/ C port of the reference time loop + adjoint, OpenMP over {cores} host threads, {pns} shots x {pnt} steps of the "
+                      f"{args.workload} grid, warm mean of {max(args.steps, 1)}, {port_s:.1f} s each"}
+    elastic = wl.get("kind") == "elastic"
+    ref_cuda = None
+    if ref_loader.available():
+        ns, nt = (2, 20) if elastic else (2, 100)
+        try:
+            val, sec = reference_gradient_sample(wl, ns, nt, "cpu", reps=max(args.steps, 1), warmup=max(args.warmup, 1))
+            kind = "reference"
+            sample = (f"unmodified reference (ADFWI propagator.forward + Misfit_waveform_L2 + loss.backward(), checkpoint_segments=4, torch "
+                      f"{cores} threads, device='cpu'), {ns} shots x {nt} steps of the {args.workload} grid, {sec:.1f} s per gradient")
+        except Exception as e:       # an unusable staging must not take the arm down: fall back to the port
+            val, sec, kind, sample = port_v, port_s, "port", port["sample"] + f" (reference failed: {type(e).__name__}: {e})"
+        try:
+            import torch
+            if torch.cuda.is_available():
+                cns, cnt = (2, 50) if elastic else (4, 100)
+                cv, cs = reference_gradient_sample(wl, cns, cnt, "cuda:0", reps=2, warmup=2)
+                ref_cuda = {"value": cv / 1e9, "unit": "Gcell-updates/s", "seconds_per_gradient": cs,
+                            "sample": f"unmodified reference with device='cuda:0' (eager ATen kernels + autograd tape), {cns} shots x {cnt} steps of the {args.workload} grid"}
+        except Exception as e:
+            ref_cuda = {"unavailable": f"{type(e).__name__}: {e}"}
+    else:
+        val, sec, kind, sample = port_v, port_s, "port", port["sample"]
+        ns, nt = pns, pnt
+    val_g = val / 1e9
     line = {
-        "impl": "reference", "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": val,
+        "impl": "reference", "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": val_g,
         "unit": "Gcell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "sample": f"{ns} shots x {nt} steps of the same padded grid"},
-        "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle/ C port of the reference time loop + adjoint, OpenMP over {cores} host threads, "
-                                   f"{ns} shots x {nt} steps of the {args.workload} grid per step"},
-        "e2e": {"value": val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": val_g, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "sample": sample},
+        "port": port, "reference_cuda": ref_cuda,
+        "e2e": {"value": val_g, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -371,8 +497,7 @@ def run_b200(args, wl):
                                 "tile walk and the working set of small grids stays in L2, so `achieved` can exceed the DRAM traffic "
                                 "actually moved (see `traffic`) and, on long tile walks, the copy-bandwidth `peak`",
                         "per_kernel_avg_ms": avg}
-        cns, cnt = cpu_sample_size()
-        cpu_v, cpu_s = cpu_gradient_sample(wl, cns, cnt)
+        cpu_base = cpu_baseline_entry(args, wl)
         line = {
             "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -386,9 +511,7 @@ def run_b200(args, wl):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(lt.item()),
             "roofline": roof,
-            "cpu_baseline": {"value": cpu_v / 1e9, "unit": "Gcell-updates/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"oracle/ C port (OpenMP, all host threads), {cns} shots x {cnt} steps of the {args.workload} grid, "
-                                       f"forward+adjoint, {cpu_s:.1f} s"},
+            "cpu_baseline": cpu_base,
             "clocks": clk,
         }
         print(json.dumps(line), flush=True)
@@ -551,8 +674,7 @@ def run_b200_elastic(args, wl):
                     "frac_by_sweep": {"forward_recording": B_fwd * cells / (fwd * 1e-3) / 1e9 / peak,
                                       "adjoint": B_adj * cells / (adj * 1e-3) / 1e9 / peak},
                     "per_kernel_avg_ms": avg}
-        cns, cnt = cpu_sample_size()
-        cpu_v, cpu_s = cpu_gradient_sample(wl, cns, cnt)
+        cpu_base = cpu_baseline_entry(args, wl)
         if roof is not None and args.abc != "PML":
             # the generic kernels advance the library's own shot groups, not the whole batch, per launch: only the
             # whole-gradient fraction is meaningful here
@@ -573,9 +695,7 @@ def run_b200_elastic(args, wl):
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(lt.item()), "roofline": roof,
-            "cpu_baseline": {"value": cpu_v / 1e9, "unit": "Gcell-updates/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"oracle/ C port (OpenMP, all host threads), {cns} shots x {cnt} steps of the {args.workload} grid, "
-                                       f"forward+adjoint, {cpu_s:.1f} s"},
+            "cpu_baseline": cpu_base,
             "clocks": clk,
         }
         print(json.dumps(line), flush=True)

@@ -1,6 +1,6 @@
 """Dev-time loader for the upstream ADFWI reference (TEST INFRASTRUCTURE ONLY).
 
-Imports the unmodified reference from ``$ADFWI_REF`` or ``/root/reference`` with the
+Imports the unmodified reference from ``$ADFWI_REF``, ``/root/reference`` or ``baseline/_ref`` with the
 plotting / IO third-party modules it does not need on the hot path replaced by
 ``MagicMock`` stubs.  Used only by ``tests/golden/make_golden.py``
 and by the optional ``tests/test_reference_live.py`` (skipped when the reference tree is
@@ -17,8 +17,13 @@ _STUBS = [
 ]
 
 
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
 def reference_root():
-    for cand in (os.environ.get("ADFWI_REF"), "/root/reference"):
+    """$ADFWI_REF, /root/reference (the build container), then the copy staged for the GPU box by
+    baseline/stage_reference.py (git-ignored, travels with the gpurun snapshot)."""
+    for cand in (os.environ.get("ADFWI_REF"), "/root/reference", _STAGED):
         if cand and os.path.isdir(os.path.join(cand, "ADFWI", "propagator")):
             return cand
     return None

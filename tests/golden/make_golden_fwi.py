@@ -26,7 +26,9 @@ def ricker_integral(nt, dt, f0):
     return np.cumsum((1 - 2 * a) * np.exp(-a)) * dt
 
 
-def main():
+def build(device="cpu"):
+    """The reference objects of the fixture on ``device``: returns (AcousticFWI instance, model, propagator, inputs dict).
+    Shared with tests/test_reference_patch_gpu.py, which runs the same script on the GPU after adfwi_b200.patch()."""
     ref_loader.load()
     from ADFWI.model import AcousticModel
     from ADFWI.survey import Source, Receiver, Survey, SeismicData
@@ -61,10 +63,10 @@ def main():
 
     def model(vp, grad):
         return AcousticModel(0, 0, nx, nz, dx, dz, vp.copy(), (310.0 * vp.astype(np.float64) ** 0.25).astype(np.float32),
-                             vp_bound=None, vp_grad=grad, free_surface=True, abc_type="PML", nabc=nabc, device="cpu")
+                             vp_bound=None, vp_grad=grad, free_surface=True, abc_type="PML", nabc=nabc, device=device)
 
     sv = survey()
-    true_prop = AcousticPropagator(model(vp_true, False), sv, device="cpu")
+    true_prop = AcousticPropagator(model(vp_true, False), sv, device=device)
     with torch.no_grad():
         obs = true_prop.forward()
     data = SeismicData(sv)
@@ -72,12 +74,21 @@ def main():
     obs_p = np.array(data.data["p"], dtype=np.float32)
 
     m = model(vp_init, True)
-    prop = AcousticPropagator(m, sv, device="cpu")
+    prop = AcousticPropagator(m, sv, device=device)
     opt = torch.optim.SGD(m.parameters(), lr=0.01)
     sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
     gp = GradProcessor(grad_mute=6, grad_smooth=2, grad_mask=None, norm_grad=True, forw_illumination=True, marine_or_land="Marine")
     fwi = AcousticFWI(propagator=prop, model=m, optimizer=opt, scheduler=sched, loss_fn=Misfit_waveform_L2(dt=1), obs_data=data,
                       gradient_processor=gp, waveform_normalize=True, cache_result=True, save_fig_epoch=-1)
+    inputs = dict(nz=nz, nx=nx, nabc=nabc, nt=nt, dx=dx, dz=dz, dt=dt, f0=f0, vp_true=vp_true, vp_init=vp_init, rho=rho, wavelet=wav,
+                  src_x=src_x, src_z=src_z, rcv_x=rcv_x, rcv_z=rcv_z, obs_p=obs_p)
+    return fwi, m, prop, inputs
+
+
+def main():
+    fwi, m, prop, inp = build("cpu")
+    nz, nx, nabc, nt, dx, dz, dt, f0 = (inp[k] for k in ("nz", "nx", "nabc", "nt", "dx", "dz", "dt", "f0"))
+    vp_true, vp_init, rho, wav, src_x, src_z, rcv_x, rcv_z, obs_p = (inp[k] for k in ("vp_true", "vp_init", "rho", "wavelet", "src_x", "src_z", "rcv_x", "rcv_z", "obs_p"))
     fwi.forward(iteration=3, batch_size=2, checkpoint_segments=1)
     out = dict(nz=nz, nx=nx, nabc=nabc, nt=nt, dx=dx, dz=dz, dt=dt, f0=f0, vp_true=vp_true, vp_init=vp_init, rho=rho, wavelet=wav,
                src_x=src_x, src_z=src_z, rcv_x=rcv_x, rcv_z=rcv_z, obs_p=obs_p, damp=np.array(prop.damp.cpu().numpy()),

@@ -23,7 +23,9 @@ def ricker_integral(nt, dt, f0):
     return np.cumsum((1 - 2 * a) * np.exp(-a)) * dt
 
 
-def main():
+def build(device="cpu"):
+    """The reference objects of the fixture on ``device``: returns (ElasticFWI instance, model, propagator, inputs dict).
+    Shared with tests/test_reference_patch_gpu.py, which runs the same script on the GPU after adfwi_b200.patch()."""
     ref_loader.load()
     from ADFWI.model import IsotropicElasticModel
     from ADFWI.survey import Source, Receiver, Survey, SeismicData
@@ -57,10 +59,10 @@ def main():
 
     def model(vp, grad):
         return IsotropicElasticModel(0, 0, nx, nz, dx, dz, vp.copy(), mk_vs(vp), mk_rho(vp), vp_grad=grad, vs_grad=grad, rho_grad=grad,
-                                     free_surface=True, abc_type="PML", nabc=nabc, auto_update_rho=False, auto_update_vp=False, device="cpu")
+                                     free_surface=True, abc_type="PML", nabc=nabc, auto_update_rho=False, auto_update_vp=False, device=device)
 
     sv = survey()
-    true_prop = ElasticPropagator(model(vp_true, False), sv, device="cpu")
+    true_prop = ElasticPropagator(model(vp_true, False), sv, device=device)
     with torch.no_grad():
         obs = true_prop.forward(fd_order=4)
     data = SeismicData(sv)
@@ -68,13 +70,24 @@ def main():
     obs_np = {k: np.array(data.data[k], dtype=np.float32) for k in ("vx", "vz")}
 
     m = model(vp_init, True)
-    prop = ElasticPropagator(m, sv, device="cpu")
+    prop = ElasticPropagator(m, sv, device=device)
     opt = torch.optim.SGD(m.parameters(), lr=0.01)
     sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
     gp = GradProcessor(grad_mute=4, grad_smooth=2, grad_mask=None, norm_grad=True, forw_illumination=True, marine_or_land="Marine")
     fwi = ElasticFWI(propagator=prop, model=m, optimizer=opt, scheduler=sched, loss_fn=Misfit_waveform_L2(dt=1), obs_data=data,
                      gradient_processor=gp, waveform_normalize=True, cache_result=True, cache_gradient=True, save_fig_epoch=-1,
                      inversion_component=["vx", "vz"])
+    inputs = dict(nz=nz, nx=nx, nabc=nabc, nt=nt, dx=dx, dz=dz, dt=dt, f0=f0, vp_init=vp_init, vs_init=mk_vs(vp_init), rho_init=mk_rho(vp_init),
+                  wavelet=wav, src_x=src_x, src_z=src_z, rcv_x=rcv_x, rcv_z=rcv_z, obs_vx=obs_np["vx"], obs_vz=obs_np["vz"])
+    return fwi, m, prop, inputs
+
+
+def main():
+    fwi, m, prop, inp = build("cpu")
+    nz, nx, nabc, nt, dx, dz, dt, f0 = (inp[k] for k in ("nz", "nx", "nabc", "nt", "dx", "dz", "dt", "f0"))
+    vp_init, wav, src_x, src_z, rcv_x, rcv_z = (inp[k] for k in ("vp_init", "wavelet", "src_x", "src_z", "rcv_x", "rcv_z"))
+    mk_vs = lambda v: inp["vs_init"]; mk_rho = lambda v: inp["rho_init"]
+    obs_np = {"vx": inp["obs_vx"], "vz": inp["obs_vz"]}
     fwi.forward(iteration=2, fd_order=4, batch_size=2, checkpoint_segments=1)
     final = {k: getattr(m, k).detach().cpu().numpy().copy() for k in ("vp", "vs", "rho")}
     out = dict(nz=nz, nx=nx, nabc=nabc, nt=nt, dx=dx, dz=dz, dt=dt, f0=f0, vp_init=vp_init, vs_init=mk_vs(vp_init), rho_init=mk_rho(vp_init),
