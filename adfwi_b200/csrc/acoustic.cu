@@ -427,16 +427,16 @@ static int ac_forward_step(const AcPlan& P, cudaStream_t st, int sb, int se, int
 
 using namespace adfwi;
 
-// The fused TMA pipeline (acoustic_fused.cu) is the default; the generic kernels of this file run
-// when the density gradient is wanted (it needs the post-step pressure history) or when the caller
-// sets bit 0 of desc->reserved[0] (used by the tests to cross-check the two pipelines).
+// The fused TMA pipeline (acoustic_fused.cu) is the default, with or without the density gradient; the
+// generic kernels of this file run when the caller sets bit 0 of desc->reserved[0] (used by the tests to
+// cross-check the two pipelines) or for grids beyond the fused path's index packing.
 static bool ac_use_fused(const adfwi_acoustic_desc* d)
 {
 #ifdef ADFWI_HOST_EMUL
     (void)d; return false;
 #else
     if (d->nzp >= 32768 || d->nxp >= 65536) return false;      // the fused path packs receiver cells as (z<<16)|x
-    return !(d->save_history && d->need_g_alpha2) && !(d->reserved[0] & 1);
+    return !(d->reserved[0] & 1);
 #endif
 }
 
@@ -555,7 +555,7 @@ extern "C" int adfwi_acoustic_backward(const adfwi_acoustic_desc* desc,
     if (ac_use_fused(desc)) {
         if (workspace_bytes < acf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
         const float* coef[5] = {alpha1, kappa1, alpha2, kappa2, kappa3};
-        return acf_backward(desc, coef, src_v, src_x, src_z, rcv_x, rcv_z, g_rcv_p, g_rcv_u, g_rcv_w, g_alpha1, g_src_v, workspace, st);
+        return acf_backward(desc, coef, src_v, src_x, src_z, rcv_x, rcv_z, g_rcv_p, g_rcv_u, g_rcv_w, g_alpha1, g_alpha2, g_src_v, workspace, st);
     }
 #endif
     if (workspace_bytes < P.bytes) return ADFWI_E_WORKSPACE;

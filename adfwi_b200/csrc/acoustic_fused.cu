@@ -29,7 +29,8 @@
 // Same arithmetic and association as the generic kernels in acoustic.cu (-fmad=false): forward
 // records stay bit-identical to the CPU reference.
 //
-// Used when the density gradient is not requested; otherwise acoustic.cu's generic kernels run.
+// The density gradient (g_alpha2) rides on the same pair: ac_fwd_fused<.., SAVE2> stores D+x p and D+z p of the new pressure,
+// ac_adj_fused<.., G2> accumulates -(mu_u * D+x p + mu_w * D+z p); the division by alpha2 happens once, in acf_reduce_g2.
 #include "common.cuh"
 #ifndef ADFWI_HOST_EMUL
 #include "tma.cuh"
@@ -77,6 +78,7 @@ struct FwdArgs {
     float *p_out, *u_out, *w_out;
     const float* src_v; const int64_t *sx, *sz;
     float* hist; int hist_len, tl, it;
+    float *hist_dx, *hist_dz;         // density gradient: D+x p and D+z p of the post-step pressure (same indexing as hist)
     int nr; RcvBuckets rb;
     float *rcv_p, *rcv_u, *rcv_w;
     float *ill_p, *ill_u; int acc_u;
@@ -88,9 +90,10 @@ struct AdjArgs {
     float *lp_out, *lu_out, *lw_out;
     const int64_t *sx, *sz;
     const float* hist; int hist_len, tl, it;
+    const float *hist_dx, *hist_dz;
     int nr; RcvBuckets rb;
     const float *gp, *gu, *gw;
-    float* g1part; float* g_src;
+    float* g1part; float* g2part; float* g_src;
     int s_begin, s_end, chunk, nchunks;
 };
 
@@ -178,7 +181,7 @@ struct Roles {
 // ------------------------------------------------------------------------------------------
 // forward: one tile, shots [s_lo, s_hi)
 // ------------------------------------------------------------------------------------------
-template <bool FS, bool SAVE, bool ILLUM, bool PML>
+template <bool FS, bool SAVE, bool SAVE2, bool ILLUM, bool PML>
 __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensorMap* tm_u, const CUtensorMap* tm_w,
                                          const FGeom& g, const FwdArgs& a, unsigned char* smem_raw, uint64_t* bar,
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx, float* s_sv,
@@ -313,15 +316,25 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
                 const float4 p0 = P[j + 1], pm1 = P[j], pp1 = P[j + 2], pp2 = P[j + 3];
                 const float4 uo = ld4(us + R.so2 + j * RX), wo = ld4(ws + R.so2 + j * RX);
                 const float4 au = AU[j], aw = PML ? AW[j] : AU[j];
-                float4 du, dw;
-                du.x = au.x * (c1 * (p0.y - p0.x) + c2 * (p0.z - pL));
-                du.y = au.y * (c1 * (p0.z - p0.y) + c2 * (p0.w - p0.x));
-                du.z = au.z * (c1 * (p0.w - p0.z) + c2 * (pR.x - p0.y));
-                du.w = au.w * (c1 * (pR.x - p0.w) + c2 * (pR.y - p0.z));
-                dw.x = aw.x * (c1 * (pp1.x - p0.x) + c2 * (pp2.x - pm1.x));
-                dw.y = aw.y * (c1 * (pp1.y - p0.y) + c2 * (pp2.y - pm1.y));
-                dw.z = aw.z * (c1 * (pp1.z - p0.z) + c2 * (pp2.z - pm1.z));
-                dw.w = aw.w * (c1 * (pp1.w - p0.w) + c2 * (pp2.w - pm1.w));
+                float4 dxp, dzp, du, dw;      // D+x p, D+z p of the new pressure (acoustic_kernels.py:139-160)
+                dxp.x = c1 * (p0.y - p0.x) + c2 * (p0.z - pL);
+                dxp.y = c1 * (p0.z - p0.y) + c2 * (p0.w - p0.x);
+                dxp.z = c1 * (p0.w - p0.z) + c2 * (pR.x - p0.y);
+                dxp.w = c1 * (pR.x - p0.w) + c2 * (pR.y - p0.z);
+                dzp.x = c1 * (pp1.x - p0.x) + c2 * (pp2.x - pm1.x);
+                dzp.y = c1 * (pp1.y - p0.y) + c2 * (pp2.y - pm1.y);
+                dzp.z = c1 * (pp1.z - p0.z) + c2 * (pp2.z - pm1.z);
+                dzp.w = c1 * (pp1.w - p0.w) + c2 * (pp2.w - pm1.w);
+                du.x = au.x * dxp.x; du.y = au.y * dxp.y; du.z = au.z * dxp.z; du.w = au.w * dxp.w;
+                dw.x = aw.x * dzp.x; dw.y = aw.y * dzp.y; dw.z = aw.z * dzp.z; dw.w = aw.w * dzp.w;
+                if (SAVE && SAVE2) {          // what the density gradient needs: g_alpha2 -= lambda_u * D+x p + lambda_w * D+z p
+                    const int gz = gz2 + j;
+                    if (col2ok && gz < g.nzp) {
+                        const size_t ho = ((size_t)s * a.hist_len + a.tl) * g.plane + (size_t)gz * ld + gx2;
+                        __stcs(reinterpret_cast<float4*>(a.hist_dx + ho), dxp);
+                        __stcs(reinterpret_cast<float4*>(a.hist_dz + ho), dzp);
+                    }
+                }
                 if (PML) {
                     uv[j].x = T2[j].x * uo.x - du.x; uv[j].y = T2[j].y * uo.y - du.y; uv[j].z = T2[j].z * uo.z - du.z; uv[j].w = T2[j].w * uo.w - du.w;
                     wv[j].x = T3[j].x * wo.x - dw.x; wv[j].y = T3[j].y * wo.y - dw.y; wv[j].z = T3[j].z * wo.z - dw.z; wv[j].w = T3[j].w * wo.w - dw.w;
@@ -379,7 +392,7 @@ __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensor
     }
 }
 
-template <bool FS, bool SAVE, bool ILLUM>
+template <bool FS, bool SAVE, bool SAVE2, bool ILLUM>
 __global__ void __launch_bounds__(NTHREADS, 2)
 ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_u,
              const __grid_constant__ CUtensorMap tm_w, const FGeom g, const FwdArgs a)
@@ -404,8 +417,8 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
         const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) fwd_tile<FS, SAVE, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk, first);
-        else                fwd_tile<FS, SAVE, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk, first);
+        if (a.tflags[tile]) fwd_tile<FS, SAVE, SAVE2, ILLUM, true>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk, first);
+        else                fwd_tile<FS, SAVE, SAVE2, ILLUM, false>(&tm_p, &tm_u, &tm_w, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, s_sv, R, tid, tile, s_lo, s_hi, chunk, first);
         __syncthreads();      // per-shot scalars and stages are reused by the next item
     }
 }
@@ -420,7 +433,7 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 // only at the thread's own cells (phase 2) and phase 1 -- lambda_p1 = lambda_p + D+z^T(-mu_w) + D+x^T(-mu_u)
 // -- needs no coefficient at all.  Cells outside a region have alpha2 = 0 there and never feed back.
 // ------------------------------------------------------------------------------------------
-template <bool FS, bool PML>
+template <bool FS, bool PML, bool G2>
 __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw,
                                          const FGeom& g, const AdjArgs& a, unsigned char* smem_raw, uint64_t* bar,
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx,
@@ -458,9 +471,9 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
             }
         }
     }
-    float4 gacc[4];
+    float4 gacc[4], g2acc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 4; ++j) { gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f); g2acc[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
     const bool inject = have_g && a.rb.nbr[tile];
     const bool col2ok = gx2 < ld;
     if (first) {
@@ -611,6 +624,19 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
                 // g_alpha1 -= lambda_p1 * S  (masked to the P region when reduced)
                 gacc[j].x = gacc[j].x - qp.x * Sh[j].x; gacc[j].y = gacc[j].y - qp.y * Sh[j].y;
                 gacc[j].z = gacc[j].z - qp.z * Sh[j].z; gacc[j].w = gacc[j].w - qp.w * Sh[j].w;
+                if (G2) {
+                    // density gradient (4T, 5T): g_alpha2 -= lambda_u * D+x p + lambda_w * D+z p with the post-injection, post-6T
+                    // cotangents.  The staged state is mu = alpha2 * lambda (zero outside a field's region), so the sum of
+                    // mu * D p is accumulated here and divided by alpha2 once, when the partial planes are reduced.
+                    float4 hu = make_float4(0.f, 0.f, 0.f, 0.f), hw = hu;
+                    if (col2ok && gz < g.nzp) {
+                        const size_t ho = ((size_t)s * a.hist_len + a.tl) * g.plane + (size_t)gz * ld + gx2;
+                        hu = __ldcs(reinterpret_cast<const float4*>(a.hist_dx + ho));
+                        hw = __ldcs(reinterpret_cast<const float4*>(a.hist_dz + ho));
+                    }
+                    g2acc[j].x = g2acc[j].x - (luo.x * hu.x + lwo.x * hw.x); g2acc[j].y = g2acc[j].y - (luo.y * hu.y + lwo.y * hw.y);
+                    g2acc[j].z = g2acc[j].z - (luo.z * hu.z + lwo.z * hw.z); g2acc[j].w = g2acc[j].w - (luo.w * hu.w + lwo.w * hw.w);
+                }
             }
         }
         if (inject || (FS && tzi == 0)) fence_proxy_async();   // generic-proxy writes to the stage precede its TMA refill
@@ -621,11 +647,14 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int gz = gz2 + j;
-        if (col2ok && gz < g.nzp) red4(a.g1part + (size_t)chunk * g.plane + (size_t)gz * ld + gx2, gacc[j]);
+        if (col2ok && gz < g.nzp) {
+            red4(a.g1part + (size_t)chunk * g.plane + (size_t)gz * ld + gx2, gacc[j]);
+            if (G2) red4(a.g2part + (size_t)chunk * g.plane + (size_t)gz * ld + gx2, g2acc[j]);
+        }
     }
 }
 
-template <bool FS>
+template <bool FS, bool G2>
 __global__ void __launch_bounds__(NTHREADS, 2)
 ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ CUtensorMap tm_lu,
              const __grid_constant__ CUtensorMap tm_lw, const FGeom g, const AdjArgs a)
@@ -649,8 +678,8 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
         const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) adj_tile<FS, true>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
-        else                adj_tile<FS, false>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
+        if (a.tflags[tile]) adj_tile<FS, true, G2>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
+        else                adj_tile<FS, false, G2>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
         __syncthreads();
     }
 }
@@ -760,6 +789,23 @@ __global__ void acf_reduce_parts(int nzp, int nxp, int ld, int fs, int nparts, c
     out[(size_t)z * nxp + x] = acc;
 }
 
+// density gradient: the partial planes hold -sum_t (mu_u * D+x p + mu_w * D+z p) with mu = alpha2 * lambda; divide by the
+// caller's alpha2 on the union of the U and W update regions (mu is identically zero outside a field's region)
+__global__ void acf_reduce_g2(int nzp, int nxp, int ld, int fs, int nparts, const float* __restrict__ part, const float* __restrict__ a2,
+                              float* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= nxp || z >= nzp) return;
+    const bool inU = (z >= fs) && (z < nzp - 1) && (x >= 1) && (x < nxp - 2);
+    const bool inW = (z >= fs) && (z < nzp - 2) && (x >= 1) && (x < nxp - 1);
+    float acc = 0.f;
+    if (inU || inW) {
+        for (int k = 0; k < nparts; ++k) acc += part[((size_t)k * nzp + z) * ld + x];
+        acc = acc / a2[(size_t)z * nxp + x];
+    }
+    out[(size_t)z * nxp + x] = acc;
+}
+
 __global__ void acf_sumsq(size_t n, size_t plane, int s_begin, int s_end, const float* __restrict__ f, float* __restrict__ out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -803,7 +849,7 @@ int acf_num_sms()
 
 struct FPlan {
     FGeom g;
-    int ns, nr, FS, save, n_segments;
+    int ns, nr, FS, save, need_g2, n_segments;
     int K, nseg, nckpt, G;
     int chunk, nchunks;             // shots one CTA walks through per tile; chunks per full group
     int cprows; size_t cpplane;
@@ -811,7 +857,7 @@ struct FPlan {
     unsigned char* tflags;
     float *st[2][3];                // p,u,w ping-pong
     float *lam[2][3];               // lambda ping-pong
-    float *hist, *ckpt, *g1part, *ill_p, *ill_u, *ill_w;
+    float *hist, *hist_dx, *hist_dz, *ckpt, *g1part, *g2part, *ill_p, *ill_u, *ill_w;
     int *rcv_cnt, *rcv_start, *rcv_cursor, *rcv_id, *rcv_zx; unsigned char* rcv_nbr;
     size_t bytes;
 };
@@ -830,6 +876,7 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
     g.c1 = d->c1; g.c2 = d->c2; g.dt = d->dt;
     P->ns = d->ns; P->nr = d->nr; P->FS = d->free_surface ? 1 : 0;
     P->save = d->save_history ? 1 : 0;
+    P->need_g2 = (d->save_history && d->need_g_alpha2) ? 1 : 0;
     P->n_segments = d->n_segments > 0 ? d->n_segments : 1;
     int K = d->ckpt_interval;
     if (K <= 0 || K >= d->nt) K = d->nt;
@@ -856,13 +903,15 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
     P->rcv_cnt = cv.take<int>(ntiles + 1); P->rcv_start = cv.take<int>(ntiles + 1); P->rcv_cursor = cv.take<int>(ntiles + 1);
     P->rcv_id = cv.take<int>(d->nr > 0 ? d->nr : 1); P->rcv_zx = cv.take<int>(d->nr > 0 ? d->nr : 1);
     P->rcv_nbr = cv.take<unsigned char>(ntiles);
-    P->hist = P->ckpt = P->g1part = nullptr;
+    P->hist = P->hist_dx = P->hist_dz = P->ckpt = P->g1part = P->g2part = nullptr;
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->lam[b][f] = nullptr;
     if (P->save) {
         for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->lam[b][f] = cv.take<float>(sp);
         P->g1part = cv.take<float>((size_t)P->nchunks * g.plane);
+        if (P->need_g2) P->g2part = cv.take<float>((size_t)P->nchunks * g.plane);
         if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * 3 * sp);
         P->hist = cv.take<float>((size_t)K * sp);
+        if (P->need_g2) { P->hist_dx = cv.take<float>((size_t)K * sp); P->hist_dz = cv.take<float>((size_t)K * sp); }
     }
     P->bytes = cv.off;
     return ADFWI_OK;
@@ -969,15 +1018,18 @@ int acf_forward_step(const FPlan& P, const StepMaps& M, cudaStream_t st, int cur
     a.p_out = P.st[cur ^ 1][0]; a.u_out = P.st[cur ^ 1][1]; a.w_out = P.st[cur ^ 1][2];
     a.src_v = src_v; a.sx = sx; a.sz = sz;
     a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it;
+    a.hist_dx = P.hist_dx; a.hist_dz = P.hist_dz;
     a.nr = rcv_p ? P.nr : 0; a.rb = acf_bucket_ptrs(P);
     a.rcv_p = rcv_p; a.rcv_u = rcv_u; a.rcv_w = rcv_w;
     a.ill_p = P.ill_p; a.ill_u = P.ill_u; a.acc_u = acc_u;
     a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
     const int grid = acf_grid(P, se - sb, &a.nchunks);
     TimedLaunch tl_(KC_AC_FWD_FUSED, st);
-#define LF(FSv, SVv, ILv) ADFWI_CUDA(acf_launch(ac_fwd_fused<FSv, SVv, ILv>, grid, FWD_SMEM, st, acf_use_pdl(), M.st[cur][0], M.st[cur][1], M.st[cur][2], g, a))
-    if (P.FS) { if (save) { if (illum) LF(true, true, true); else LF(true, true, false); } else { if (illum) LF(true, false, true); else LF(true, false, false); } }
-    else      { if (save) { if (illum) LF(false, true, true); else LF(false, true, false); } else { if (illum) LF(false, false, true); else LF(false, false, false); } }
+#define LF(FSv, SVv, S2v, ILv) ADFWI_CUDA(acf_launch(ac_fwd_fused<FSv, SVv, S2v, ILv>, grid, FWD_SMEM, st, acf_use_pdl(), M.st[cur][0], M.st[cur][1], M.st[cur][2], g, a))
+#define LF2(FSv, ILv) do { if (!save) LF(FSv, false, false, ILv); else if (P.need_g2) LF(FSv, true, true, ILv); else LF(FSv, true, false, ILv); } while (0)
+    if (P.FS) { if (illum) LF2(true, true); else LF2(true, false); }
+    else      { if (illum) LF2(false, true); else LF2(false, false); }
+#undef LF2
 #undef LF
     ADFWI_LAUNCH_CHECK();
     return ADFWI_OK;
@@ -993,11 +1045,12 @@ int acf_init_kernels()
     bool& done = done_dev[dev];
     if (done) return 0;
     int rc = 0;
-    rc |= acf_set_smem(ac_fwd_fused<true, true, true>, FWD_SMEM);   rc |= acf_set_smem(ac_fwd_fused<true, true, false>, FWD_SMEM);
-    rc |= acf_set_smem(ac_fwd_fused<true, false, true>, FWD_SMEM);  rc |= acf_set_smem(ac_fwd_fused<true, false, false>, FWD_SMEM);
-    rc |= acf_set_smem(ac_fwd_fused<false, true, true>, FWD_SMEM);  rc |= acf_set_smem(ac_fwd_fused<false, true, false>, FWD_SMEM);
-    rc |= acf_set_smem(ac_fwd_fused<false, false, true>, FWD_SMEM); rc |= acf_set_smem(ac_fwd_fused<false, false, false>, FWD_SMEM);
-    rc |= acf_set_smem(ac_adj_fused<true>, ADJ_SMEM);               rc |= acf_set_smem(ac_adj_fused<false>, ADJ_SMEM);
+#define SF(FSv, SVv, S2v) do { rc |= acf_set_smem(ac_fwd_fused<FSv, SVv, S2v, true>, FWD_SMEM); rc |= acf_set_smem(ac_fwd_fused<FSv, SVv, S2v, false>, FWD_SMEM); } while (0)
+    SF(true, true, true); SF(true, true, false); SF(true, false, false);
+    SF(false, true, true); SF(false, true, false); SF(false, false, false);
+#undef SF
+    rc |= acf_set_smem(ac_adj_fused<true, true>, ADJ_SMEM);  rc |= acf_set_smem(ac_adj_fused<true, false>, ADJ_SMEM);
+    rc |= acf_set_smem(ac_adj_fused<false, true>, ADJ_SMEM); rc |= acf_set_smem(ac_adj_fused<false, false>, ADJ_SMEM);
     if (!rc) done = true;
     return rc;
 }
@@ -1076,9 +1129,9 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
 
 int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const float* src_v, const int64_t* sx, const int64_t* sz,
                  const int64_t* rx, const int64_t* rz, const float* gp, const float* gu, const float* gw,
-                 float* g_alpha1, float* g_src, void* ws, cudaStream_t st)
+                 float* g_alpha1, float* g_alpha2, float* g_src, void* ws, cudaStream_t st)
 {
-    (void)coef; (void)rx; (void)rz;
+    (void)rx; (void)rz;
     FPlan P;
     acf_make_plan(d, ws, &P, 148);
     const FGeom& g = P.g;
@@ -1090,6 +1143,7 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
     // the coefficient pack, tile flags and receiver buckets were left in the workspace by the forward call
     const int nt = g.nt;
     ADFWI_CUDA(cudaMemsetAsync(P.g1part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
+    if (P.need_g2) ADFWI_CUDA(cudaMemsetAsync(P.g2part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
         const size_t off = (size_t)sb * g.plane, cnt = (size_t)(se - sb) * g.plane * sizeof(float);
@@ -1117,13 +1171,16 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
                 a.cp = acf_pack_ptrs(P); a.tflags = P.tflags;
                 a.lp_out = P.lam[lcur ^ 1][0]; a.lu_out = P.lam[lcur ^ 1][1]; a.lw_out = P.lam[lcur ^ 1][2];
                 a.sx = sx; a.sz = sz; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it;
+                a.hist_dx = P.hist_dx; a.hist_dz = P.hist_dz;
                 a.nr = P.nr; a.rb = acf_bucket_ptrs(P); a.gp = gp; a.gu = gu; a.gw = gw;
-                a.g1part = P.g1part; a.g_src = g_src; a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
+                a.g1part = P.g1part; a.g2part = P.g2part; a.g_src = g_src; a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
                 const int grid = acf_grid(P, se - sb, &a.nchunks);
                 {
                     TimedLaunch tl_(KC_AC_ADJ_FUSED, st);
-                    if (P.FS) ADFWI_CUDA(acf_launch(ac_adj_fused<true>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a));
-                    else      ADFWI_CUDA(acf_launch(ac_adj_fused<false>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a));
+#define LA(FSv, G2v) ADFWI_CUDA(acf_launch(ac_adj_fused<FSv, G2v>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a))
+                    if (P.FS) { if (P.need_g2) LA(true, true); else LA(true, false); }
+                    else      { if (P.need_g2) LA(false, true); else LA(false, false); }
+#undef LA
                 }
                 ADFWI_LAUNCH_CHECK();
                 lcur ^= 1;
@@ -1132,6 +1189,10 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
     }
     acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g1part, g_alpha1);
     ADFWI_LAUNCH_CHECK();
+    if (P.need_g2) {
+        acf_reduce_g2<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g2part, coef[2], g_alpha2);
+        ADFWI_LAUNCH_CHECK();
+    }
     return ADFWI_OK;
 }
 

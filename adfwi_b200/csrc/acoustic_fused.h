@@ -11,6 +11,6 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
                 float* illum_p, float* illum_u, float* illum_w, void* ws, cudaStream_t st);
 int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const float* src_v, const int64_t* sx, const int64_t* sz,
                  const int64_t* rx, const int64_t* rz, const float* gp, const float* gu, const float* gw,
-                 float* g_alpha1, float* g_src, void* ws, cudaStream_t st);
+                 float* g_alpha1, float* g_alpha2, float* g_src, void* ws, cudaStream_t st);
 }
 #endif

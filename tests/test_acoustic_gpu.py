@@ -90,7 +90,7 @@ def test_fused_pipeline_vp_only(golden_dir, name, cfg):
 
 
 def test_fused_large_grid_matches_generic():
-    """Multi-tile grid (several 64x32 tiles, ragged edges, many receivers): fused vs generic kernels."""
+    """Multi-tile grid (several 64x32 tiles, ragged edges, many receivers): fused vs generic kernels, vp and rho gradients."""
     from adfwi_b200.propagator import acoustic_kernels as ak
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -108,9 +108,10 @@ def test_fused_large_grid_matches_generic():
             old = dict(ak.config); ak.config.update(force_generic=mode, shots_per_group=(2 if mode else 0), shots_per_chunk=(5 if fs else 2))
             try:
                 vv = v.clone().requires_grad_(True)
-                rec = ak.forward_kernel(nx, nz, 10.0, 10.0, nt, 1e-3, nabc, fs, sx, sz, ns, src, rx, rz, rx.numel(), damp, vv, rho, device=dev)
+                rr = rho.clone().requires_grad_(True)      # density gradient: fused (SAVE2 / G2 instantiations) vs generic
+                rec = ak.forward_kernel(nx, nz, 10.0, 10.0, nt, 1e-3, nabc, fs, sx, sz, ns, src, rx, rz, rx.numel(), damp, vv, rr, device=dev)
                 ((rec["p"] * W).sum() + 1e6 * (rec["u"] * W).sum() + 1e6 * (rec["w"] * W).sum()).backward()
-                out[mode] = (rec, vv.grad.clone())
+                out[mode] = (rec, vv.grad.clone(), rr.grad.clone())
             finally:
                 ak.config.clear(); ak.config.update(old)
         for k in ("p", "u", "w"):
@@ -118,6 +119,7 @@ def test_fused_large_grid_matches_generic():
         for k in ("forward_wavefield_p", "forward_wavefield_u", "forward_wavefield_w"):
             assert rel_l2(out[False][0][k].cpu().numpy(), out[True][0][k].cpu().numpy()) < 1e-5
         assert rel_l2(out[False][1].cpu().numpy(), out[True][1].cpu().numpy()) < 1e-5, fs
+        assert rel_l2(out[False][2].cpu().numpy(), out[True][2].cpu().numpy()) < 1e-5, fs
 
 
 def test_out_of_range_indices_raise_without_a_per_call_sync(golden_dir):

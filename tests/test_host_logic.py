@@ -78,7 +78,7 @@ def test_diff_coef_bits():
 
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the driver's reference arm) runs on the host only: one JSON line with the keys the
-    contract names, timed on the oracle port."""
+    contract names, timed on the unmodified reference (when present) with the oracle port beside it."""
     import json
     import os
     import subprocess
@@ -91,5 +91,8 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Gcell-updates/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_loader
+    # the unmodified reference when its package is present (this container / staged under baseline/_ref), else the C port
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["port"]["kind"] == "port" and d["port"]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

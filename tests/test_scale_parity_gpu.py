@@ -28,8 +28,11 @@ def rel_l2(a, b):
 
 
 def l2_misfit(syn_rec, obs, dt):
+    """Misfit_waveform_L2 (fwi/misfit/L2.py:22-28).  The tiny offset keeps the derivative of the square root finite for traces
+    the wave has not reached yet (zero residual -> 0/0 = NaN in the reference's expression); the resulting cotangent is handed
+    to the CUDA path and to the oracle alike."""
     r = obs - syn_rec
-    return torch.sum(torch.sqrt(torch.sum(r * r * dt, dim=1)))
+    return torch.sum(torch.sqrt(torch.sum(r * r * dt, dim=1) + 1e-30))
 
 
 def _oracle_threads():
