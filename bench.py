@@ -761,7 +761,10 @@ def secondary_measurements(args):
         t0 = time.time()
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-            d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")][-1])
+            lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+            if not lines:
+                raise RuntimeError(f"rc {r.returncode}: " + r.stderr.strip().splitlines()[-1] if r.stderr.strip() else f"rc {r.returncode}, no output")
+            d = json.loads(lines[-1])
             roof = d.get("roofline") or {}
             out.append({"label": label, "args": " ".join(extra), "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
                         "e2e": d["e2e"]["value"], "shots_per_s": d.get("shots_per_s"), "padded_grid": d["config"]["padded_grid"], "nt": d["config"]["nt"],

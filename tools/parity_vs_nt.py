@@ -18,6 +18,13 @@ import test_scale_parity_gpu as T  # noqa: E402
 
 
 def main():
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # the helpers print their own progress lines: keep stdout for the JSON
+        out = run()
+    print(json.dumps(out, indent=1))
+
+
+def run():
     out = {"acoustic_C1_grid": {}, "elastic_vti_example_grid": {}}
     for nt in (150, 600, 1600, 4000):
         out["acoustic_C1_grid"][nt] = T._acoustic_vs_oracle(88, 200, 30, nt, 40.0, 3e-3, 5.0, ns=2, nr=200, tag=f"C1 grid nt {nt}")
@@ -25,7 +32,7 @@ def main():
                                                                   params=("eps", "delta", "vp", "vs", "rho"), tag=f"VTI example grid nt {nt}")
     out["note"] = ("relative L2 error of the gradients vs the CPU oracle (records are asserted bit-identical inside); cotangent = "
                    "dL/drecord of the L2 waveform misfit against records of the true model; bar 1e-4")
-    print(json.dumps(out, indent=1))
+    return out
 
 
 if __name__ == "__main__":
