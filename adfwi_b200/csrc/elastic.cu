@@ -727,24 +727,27 @@ static int el_backward_t(const ElPlan& P, cudaStream_t st, const ElArgs& a, cons
 
 using namespace adfwi;
 
-// The TMA-staged pipeline (elastic_fused.cu) is the default for the split-field PML; the generic
-// kernels of this file run for the sponge (ABL) boundary or when the caller sets bit 0 of
-// desc->reserved[0] (used by the tests to cross-check the two pipelines).
+// The TMA-staged pipelines (elastic_fused.cu: split-field PML; elastic_abl_fused.inl: sponge / ABL) are the
+// default; the generic kernels of this file run when the caller sets bit 0 of desc->reserved[0] (used by
+// the tests to cross-check the pipelines) or for grids beyond the fused paths' index packing.
 static bool el_use_fused(const adfwi_elastic_desc* d)
 {
 #ifdef ADFWI_HOST_EMUL
     (void)d; return false;
 #else
-    return elf_supported(d);
+    return elf_supported(d) || ela_supported(d);
 #endif
 }
+#ifndef ADFWI_HOST_EMUL
+static size_t el_fused_bytes(const adfwi_elastic_desc* d) { return d->abc_pml ? elf_workspace_bytes(d) : ela_workspace_bytes(d); }
+#endif
 
 extern "C" size_t adfwi_elastic_workspace_bytes(const adfwi_elastic_desc* desc)
 {
     ElPlan P;
     if (el_make_plan(desc, nullptr, &P) != ADFWI_OK) return 0;
 #ifndef ADFWI_HOST_EMUL
-    if (el_use_fused(desc)) return elf_workspace_bytes(desc);
+    if (el_use_fused(desc)) return el_fused_bytes(desc);
 #endif
     return P.bytes;
 }
@@ -780,7 +783,8 @@ extern "C" int adfwi_elastic_forward(const adfwi_elastic_desc* desc, const float
     cudaStream_t st = (cudaStream_t)stream;
 #ifndef ADFWI_HOST_EMUL
     if (el_use_fused(desc)) {
-        if (workspace_bytes < elf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
+        if (workspace_bytes < el_fused_bytes(desc)) return ADFWI_E_WORKSPACE;
+        if (!desc->abc_pml) return ela_forward(desc, coef, bcx, mt, src_v, src_x, src_z, rcv_x, rcv_z, rcv, illum, workspace, st);
         return elf_forward(desc, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, rcv, illum, workspace, st);
     }
 #endif
@@ -806,7 +810,8 @@ extern "C" int adfwi_elastic_backward(const adfwi_elastic_desc* desc, const floa
     cudaStream_t st = (cudaStream_t)stream;
 #ifndef ADFWI_HOST_EMUL
     if (el_use_fused(desc)) {
-        if (workspace_bytes < elf_workspace_bytes(desc)) return ADFWI_E_WORKSPACE;
+        if (workspace_bytes < el_fused_bytes(desc)) return ADFWI_E_WORKSPACE;
+        if (!desc->abc_pml) return ela_backward(desc, mt, src_v, src_x, src_z, g_rcv, g_coef, g_src_v, workspace, st);
         return elf_backward(desc, coef, bcx, bcz, mt, src_v, src_x, src_z, rcv_x, rcv_z, g_rcv, g_coef, g_src_v, workspace, st);
     }
 #endif

@@ -45,7 +45,8 @@ constexpr int NG = TX / 4;                  // float4 groups per tile row
 constexpr int RPT = 1;                      // tile rows per thread
 constexpr int NTH = NG * (TZ / RPT);        // threads per CTA: one float4 group x RPT rows each
 constexpr int CMAX = 32;                    // max shots per chunk
-constexpr int CPX = 4, CPZ = 4;             // apron of the coefficient pack
+constexpr int CPX = 8, CPZ = 8;             // apron of the coefficient pack (>= the 2NN ring of the fused reverse kernels, NN <= 3)
+constexpr int FLX = 4, FLZ = 4;             // neighbourhood of a tile that decides its class (PML factors present or not)
 constexpr int NSTAGE = 2;
 constexpr int CF = TZ * TX;                 // floats of a core (no halo) rectangle
 constexpr int CB = CF * 4;
@@ -2032,6 +2033,8 @@ elf_b(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     }
 }
 
+#include "elastic_abl_fused.inl"
+
 // ---- set-up kernels ------------------------------------------------------------------------------
 // coefficient pack: eight planes [cprows][cpld] (C11,C13,C33,C55,bx,bz,bcx,bcz), logical cell (z,x) at
 // [(z+CPZ)*cpld + x+CPX], zero outside the grid
@@ -2045,18 +2048,18 @@ __global__ void elf_pack_coefs(int nzp, int nxp, int cprows, int cpld, size_t cp
     const size_t c = in ? (size_t)z * nxp + x : 0;
     const size_t o = (size_t)zz * cpld + xx;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) pack[k * cpplane + o] = in ? src.p[k][c] : 0.f;
+    for (int k = 0; k < 8; ++k) pack[k * cpplane + o] = (in && src.p[k]) ? src.p[k][c] : 0.f;
 }
-// tile flag = 1 when any cell of the tile's neighbourhood (tile + apron) has a non-zero PML profile
+// tile flag = 1 when any cell of the tile's neighbourhood (tile + FLX / FLZ cells) has a non-zero PML profile
 __global__ void elf_tile_flags(int ntx, int cpld, size_t cpplane, const float* __restrict__ pack, unsigned char* __restrict__ flags)
 {
     const int tile = blockIdx.x;
     const int tzi = tile / ntx, txi = tile - tzi * ntx;
     const int X0 = txi * TX, Z0 = tzi * TZ;
-    const int W = TX + 2 * CPX, H = TZ + 2 * CPZ;
+    const int W = TX + 2 * FLX, H = TZ + 2 * FLZ;
     int bad = 0;
     for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
-        const size_t o = (size_t)(Z0 + i / W) * cpld + (X0 + i % W);
+        const size_t o = (size_t)(Z0 + CPZ - FLZ + i / W) * cpld + (X0 + CPX - FLX + i % W);
         if (pack[6 * cpplane + o] != 0.f || pack[7 * cpplane + o] != 0.f) bad = 1;
     }
     bad = __syncthreads_or(bad);
@@ -2583,6 +2586,325 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
     return ADFWI_OK;
 }
 
+
+// ====================================================================================================
+// sponge (ABL) pipeline: host side of ela_f / ela_b (elastic_abl_fused.inl)
+// ====================================================================================================
+struct EAPlan {
+    EGeom g;
+    int ns, nr, NN, FS, save, n_segments, nz, nx, nabc, zoff;
+    int K, nseg, nckpt, G;
+    int chunk, nchunks;
+    int cprows; size_t cpplane;
+    float* pack;
+    float* planes; int nfields;
+    float* side;                        // free-surface side buffer: [2 parities][2 rows][ns][ld]
+    float *hist, *ckpt, *gpart, *ill;
+    int* counters; int ncounters;
+    int *rcv_cnt, *rcv_start, *rcv_cursor, *rcv_id, *rcv_zx; unsigned char* rcv_nbr;
+    size_t ckpt_stride;                 // floats per checkpoint slot: 5 state planes + the side rows, all shots
+    size_t bytes;
+};
+
+int ela_make_plan(const adfwi_elastic_desc* d, void* ws, EAPlan* P, int nsm)
+{
+    EGeom& g = P->g;
+    const int NN = d->fd_order / 2;
+    g.nzp = d->nzp; g.nxp = d->nxp; g.ld = (d->nxp + 31) / 32 * 32; g.fs = d->free_surface ? 1 : 0; g.nt = d->nt; g.ns = d->ns;
+    g.ntx = cdiv(g.nxp, TX); g.ntz = cdiv(g.nzp, TZ);
+    g.cpld = g.ntx * TX + 2 * CPX;
+    g.plane = (size_t)g.nzp * g.ld;
+    g.dt = d->dt; g.dx = d->dx; g.dz = d->dz; g.dt_dx = d->dt_dx; g.dt_dz = d->dt_dz; g.half_dt = d->half_dt;
+    g.rdx = 1.0f / d->dx; g.rdz = 1.0f / d->dz;
+    g.merge = 0;
+    for (int k = 0; k < 3; ++k) g.c[k] = d->fdc[k];
+    P->cprows = g.ntz * TZ + 2 * CPZ;
+    P->cpplane = align_up((size_t)P->cprows * g.cpld, 64);
+    P->ns = d->ns; P->nr = d->nr; P->NN = NN; P->FS = g.fs; P->save = d->save_history ? 1 : 0;
+    P->n_segments = d->n_segments > 0 ? d->n_segments : 1;
+    P->nz = d->nz; P->nx = d->nx; P->nabc = d->nabc; P->zoff = d->free_surface ? NN : NN + d->nabc;
+    int K = d->ckpt_interval;
+    if (K <= 0 || K >= d->nt) K = d->nt;
+    P->K = K; P->nseg = cdiv(d->nt, K); P->nckpt = P->nseg > 2 ? P->nseg - 2 : 0;
+    int G = d->shots_per_group;
+    if (G <= 0 || G > d->ns) G = d->ns;
+    P->G = G;
+    const int ntiles = g.ntx * g.ntz;
+    int nchunks = d->reserved[1] > 0 ? cdiv(G, d->reserved[1]) : (6 * CTAS_PER_SM * nsm + ntiles - 1) / ntiles;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > G) nchunks = G;
+    int chunk = cdiv(G, nchunks);
+    if (chunk > CMAX) chunk = CMAX;
+    P->chunk = chunk; P->nchunks = cdiv(G, chunk);
+    Carver cv(ws);
+    const size_t sp = (size_t)d->ns * g.plane;
+    P->pack = cv.take<float>(8 * P->cpplane);
+    P->nfields = P->save ? A_COUNT : A_FWD_COUNT;
+    P->planes = cv.take<float>((size_t)P->nfields * sp);
+    P->side = cv.take<float>((size_t)4 * d->ns * g.ld);
+    P->ill = cv.take<float>((size_t)5 * d->nz * d->nx);
+    P->rcv_cnt = cv.take<int>(ntiles + 1); P->rcv_start = cv.take<int>(ntiles + 1); P->rcv_cursor = cv.take<int>(ntiles + 1);
+    P->rcv_id = cv.take<int>(d->nr > 0 ? d->nr : 1); P->rcv_zx = cv.take<int>(d->nr > 0 ? d->nr : 1);
+    P->rcv_nbr = cv.take<unsigned char>(ntiles);
+    P->ncounters = 3 * d->nt * cdiv(d->ns, G) + 64;
+    P->counters = cv.take<int>(P->ncounters);
+    P->hist = P->ckpt = P->gpart = nullptr;
+    P->ckpt_stride = 5 * sp + (size_t)2 * d->ns * g.ld;
+    if (P->save) {
+        P->gpart = cv.take<float>((size_t)P->nchunks * 6 * g.plane);
+        if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * P->ckpt_stride);
+        P->hist = cv.take<float>((size_t)K * ANHIST * sp);
+    }
+    P->bytes = cv.off;
+    return ADFWI_OK;
+}
+
+ECoef ela_pack_ptrs(const EAPlan& P)
+{
+    const size_t o = (size_t)CPZ * P.g.cpld + CPX;
+    ECoef c;
+    c.c11 = P.pack + 0 * P.cpplane + o; c.c13 = P.pack + 1 * P.cpplane + o; c.c33 = P.pack + 2 * P.cpplane + o; c.c55 = P.pack + 3 * P.cpplane + o;
+    c.bx = P.pack + 4 * P.cpplane + o; c.bz = P.pack + 5 * P.cpplane + o; c.bcx = P.pack + 6 * P.cpplane + o; c.bcz = P.pack + 7 * P.cpplane + o;
+    return c;
+}
+RcvB ela_bucket_ptrs(const EAPlan& P) { RcvB b; b.start = P.rcv_start; b.id = P.rcv_id; b.zx = P.rcv_zx; b.nbr = P.rcv_nbr; return b; }
+
+int ela_setup(const EAPlan& P, cudaStream_t st, const float* const* coef, const float* damp, const int64_t* rx, const int64_t* rz)
+{
+    const EGeom& g = P.g;
+    PackSrc src;
+    for (int k = 0; k < 6; ++k) src.p[k] = coef[k];
+    src.p[6] = damp; src.p[7] = nullptr;
+    elf_pack_coefs<<<dim3(cdiv(g.cpld, 128), P.cprows), 128, 0, st>>>(g.nzp, g.nxp, P.cprows, g.cpld, P.cpplane, src, P.pack);
+    ADFWI_LAUNCH_CHECK();
+    const int ntiles = g.ntx * g.ntz;
+    ADFWI_CUDA(cudaMemsetAsync(P.rcv_cnt, 0, sizeof(int) * (ntiles + 1), st));
+    if (P.nr > 0) {
+        elf_rcv_count<<<cdiv(P.nr, 128), 128, 0, st>>>(g.nzp, g.nxp, g.ntx, P.nr, rx, rz, P.rcv_cnt);
+        ADFWI_LAUNCH_CHECK();
+    }
+    elf_rcv_scan<<<1, 32, 0, st>>>(ntiles, P.rcv_cnt, P.rcv_start, P.rcv_cursor);
+    ADFWI_LAUNCH_CHECK();
+    if (P.nr > 0) {
+        elf_rcv_fill<<<cdiv(P.nr, 128), 128, 0, st>>>(g.nzp, g.nxp, g.ntx, P.nr, rx, rz, P.rcv_cursor, P.rcv_id, P.rcv_zx);
+        ADFWI_LAUNCH_CHECK();
+    }
+    elf_rcv_nbr<<<cdiv(ntiles, 128), 128, 0, st>>>(g.ntx, g.ntz, P.rcv_start, P.rcv_nbr);
+    ADFWI_LAUNCH_CHECK();
+    return ADFWI_OK;
+}
+
+struct EAMaps { CUtensorMap halo, halo2, hist; };
+
+int ela_make_maps(const EAPlan& P, EAMaps* M)
+{
+    const EGeom& g = P.g;
+    int rc = make_tmap_f32(&M->halo, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, RXH, TZ + 2 * P.NN);
+    if (rc) return rc;
+    rc = make_tmap_f32(&M->halo2, P.planes, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.nfields * P.ns, TX + 2 * (P.NN == 2 ? 4 : 8), TZ + 4 * P.NN);
+    if (rc || !P.save) return rc;
+    return make_tmap_f32(&M->hist, P.hist, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.ns * P.K * ANHIST, TX, TZ);
+}
+
+template <int NN> constexpr int af_smem() { return NSTAGE * GeoA<NN>::STAGE + TAIL_BYTES; }
+template <int NN> constexpr int ab_smem() { return NSTAGE * GeoA<NN>::STAGE + TAIL_SMALL + GeoA<NN>::FS_BYTES + 64; }
+static_assert(2 * (af_smem<3>() + 1024) <= 233472 && 2 * (ab_smem<3>() + 1024) <= 233472, "two CTAs per SM must fit in shared memory");
+
+template <int NN> int ela_init_kernels()
+{
+    static bool done_dev[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    bool& done = done_dev[dev];
+    if (done) return 0;
+    int rc = 0;
+    rc |= elf_set_smem(ela_f<NN, true, true>, af_smem<NN>());   rc |= elf_set_smem(ela_f<NN, true, false>, af_smem<NN>());
+    rc |= elf_set_smem(ela_f<NN, false, true>, af_smem<NN>());  rc |= elf_set_smem(ela_f<NN, false, false>, af_smem<NN>());
+    rc |= elf_set_smem(ela_b<NN, true>, ab_smem<NN>());         rc |= elf_set_smem(ela_b<NN, false>, ab_smem<NN>());
+    if (!rc) done = true;
+    return rc;
+}
+
+inline Walk ela_walk(const EAPlan& P, int sb, int se, int* grid)
+{
+    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = P.chunk; w.nchunks = cdiv(se - sb, P.chunk); w.counter = nullptr;
+    const int nitems = P.g.ntx * P.g.ntz * w.nchunks;
+    const int cap = CTAS_PER_SM * elf_num_sms();
+    *grid = nitems < cap ? nitems : cap;
+    return w;
+}
+
+// one forward step of shots [sb,se): reads field set *cur (and side-buffer parity *cur), writes the other one, flips *cur
+template <int NN>
+int ela_forward_step(const EAPlan& P, const EAMaps& M, cudaStream_t st, int sb, int se, int it, bool save, int tl,
+                     const EArgs& ea, float* const* rcv, int* seq, int* cur)
+{
+    if (*seq + 1 > P.ncounters) return ADFWI_E_DIMS;
+    const EGeom& g = P.g;
+    int grid;
+    AFArgs a;
+    a.w = ela_walk(P, sb, se, &grid);
+    a.w.counter = P.counters + (*seq)++;
+    a.cp = ela_pack_ptrs(P); a.planes = P.planes; a.cur = *cur; a.mt = ea.mt; a.src_v = ea.src_v; a.sx = ea.sx; a.sz = ea.sz;
+    a.hist = P.hist; a.hist_len = P.K; a.tl = tl; a.it = it;
+    a.nr = rcv ? P.nr : 0; a.rb = ela_bucket_ptrs(P);
+    for (int k = 0; k < 5; ++k) a.rcv[k] = rcv ? rcv[k] : nullptr;
+    a.side = P.side;
+    const bool pdl = elf_use_pdl();
+    {
+        TimedLaunch tl_(KC_EL_FWD_FUSED, st);
+        if (P.FS) { if (save) ADFWI_CUDA(elf_launch(ela_f<NN, true, true>, grid, af_smem<NN>(), st, pdl, M.halo, M.halo2, g, a));
+                    else      ADFWI_CUDA(elf_launch(ela_f<NN, true, false>, grid, af_smem<NN>(), st, pdl, M.halo, M.halo2, g, a)); }
+        else      { if (save) ADFWI_CUDA(elf_launch(ela_f<NN, false, true>, grid, af_smem<NN>(), st, pdl, M.halo, M.halo2, g, a));
+                    else      ADFWI_CUDA(elf_launch(ela_f<NN, false, false>, grid, af_smem<NN>(), st, pdl, M.halo, M.halo2, g, a)); }
+    }
+    ADFWI_LAUNCH_CHECK();
+    *cur ^= 1;
+    return ADFWI_OK;
+}
+
+// the five state planes (set `cur`) and the two side rows (parity `cur`) of shots [sb,se) <-> checkpoint slot
+int ela_copy_state(const EAPlan& P, cudaStream_t st, int sb, int se, float* ck, bool to_ckpt, int cur)
+{
+    const size_t sp = (size_t)P.ns * P.g.plane;
+    const size_t off = (size_t)sb * P.g.plane, cnt = (size_t)(se - sb) * P.g.plane * sizeof(float);
+    for (int f = 0; f < 5; ++f) {
+        float* a = P.planes + (size_t)((cur ? A_SET : 0) + f) * sp + off;
+        float* b = ck + (size_t)f * sp + off;
+        ADFWI_CUDA(cudaMemcpyAsync(to_ckpt ? b : a, to_ckpt ? a : b, cnt, cudaMemcpyDeviceToDevice, st));
+    }
+    const size_t srow = (size_t)P.ns * P.g.ld, soff = (size_t)sb * P.g.ld, scnt = (size_t)(se - sb) * P.g.ld * sizeof(float);
+    for (int r = 0; r < 2; ++r) {
+        float* a = P.side + (size_t)((cur ? 2 : 0) + r) * srow + soff;
+        float* b = ck + 5 * sp + (size_t)r * srow + soff;
+        ADFWI_CUDA(cudaMemcpyAsync(to_ckpt ? b : a, to_ckpt ? a : b, scnt, cudaMemcpyDeviceToDevice, st));
+    }
+    return ADFWI_OK;
+}
+int ela_zero_fields(const EAPlan& P, cudaStream_t st, int f0, int f1, int sb, int se)
+{
+    const size_t sp = (size_t)P.ns * P.g.plane;
+    if (sb == 0 && se == P.ns) return (int)cudaMemsetAsync(P.planes + (size_t)f0 * sp, 0, (size_t)(f1 - f0) * sp * sizeof(float), st);
+    for (int f = f0; f < f1; ++f)
+        ADFWI_CUDA(cudaMemsetAsync(P.planes + (size_t)f * sp + (size_t)sb * P.g.plane, 0, (size_t)(se - sb) * P.g.plane * sizeof(float), st));
+    return ADFWI_OK;
+}
+int ela_zero_state(const EAPlan& P, cudaStream_t st, int sb, int se)
+{
+    int rc = ela_zero_fields(P, st, 0, A_FWD_COUNT, sb, se);
+    if (rc) return rc;
+    const size_t srow = (size_t)P.ns * P.g.ld;
+    for (int r = 0; r < 4; ++r)
+        ADFWI_CUDA(cudaMemsetAsync(P.side + (size_t)r * srow + (size_t)sb * P.g.ld, 0, (size_t)(se - sb) * P.g.ld * sizeof(float), st));
+    return ADFWI_OK;
+}
+
+// squares of the five fields of the current state, summed over shots (elastic_kernels.py:769-774), physical cells only
+__global__ void ela_illum_acc(EGeom g, int nz, int nx, int nabc, int zoff, int sb, int se, int base, const float* __restrict__ planes, float* __restrict__ ill)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= nx || z >= nz) return;
+    const size_t c = (size_t)(z + zoff) * g.ld + (x + nabc), o = (size_t)z * nx + x, n = (size_t)nz * nx;
+    const size_t fp = (size_t)g.ns * g.plane;
+    const int order[5] = {A_TXX, A_TZZ, A_TXZ, A_VX, A_VZ};
+    for (int k = 0; k < 5; ++k) {
+        float acc = 0.f;
+        for (int s = sb; s < se; ++s) { const float v = planes[(size_t)(base + order[k]) * fp + (size_t)s * g.plane + c]; acc += v * v; }
+        ill[k * n + o] += acc;
+    }
+}
+
+template <int NN>
+int ela_forward_t(const EAPlan& P, const EAMaps& M, cudaStream_t st, const EArgs& ea, float* const* rcv, float* const* illum)
+{
+    const EGeom& g = P.g;
+    const int nt = g.nt;
+    const int csz = cdiv(nt, P.n_segments);
+    const int nphys = P.nz * P.nx;
+    if (illum) ADFWI_CUDA(cudaMemsetAsync(P.ill, 0, sizeof(float) * 5 * nphys, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(int) * P.ncounters, st));
+    int seq = 0;
+    for (int sb = 0; sb < P.ns; sb += P.G) {
+        const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
+        int rc = ela_zero_state(P, st, sb, se);
+        if (rc) return rc;
+        int cur = 0;
+        for (int it = 0; it < nt; ++it) {
+            const int seg = it / P.K, tl = it - seg * P.K;
+            if (P.save && tl == 0 && seg >= 1 && seg <= P.nseg - 2) {
+                rc = ela_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * P.ckpt_stride, true, cur);
+                if (rc) return rc;
+            }
+            const bool save = P.save && seg == P.nseg - 1;
+            rc = ela_forward_step<NN>(P, M, st, sb, se, it, save, tl, ea, P.nr > 0 ? rcv : nullptr, &seq, &cur);
+            if (rc) return rc;
+            if (illum && ((it + 1) % csz == 0 || it == nt - 1)) {
+                ela_illum_acc<<<dim3(cdiv(P.nx, 128), P.nz), 128, 0, st>>>(g, P.nz, P.nx, P.nabc, P.zoff, sb, se, cur ? A_SET : 0, P.planes, P.ill);
+                ADFWI_LAUNCH_CHECK();
+            }
+        }
+    }
+    if (illum) {
+        elf_illum_out<<<cdiv(nphys, 256), 256, 0, st>>>(nphys, P.ill, illum[0], illum[1], illum[2], illum[3], illum[4]);
+        ADFWI_LAUNCH_CHECK();
+    }
+    return ADFWI_OK;
+}
+
+template <int NN>
+int ela_backward_t(const EAPlan& P, const EAMaps& M, cudaStream_t st, const EArgs& ea, const float* const* g_rcv, float* const* g_coef, float* g_src)
+{
+    const EGeom& g = P.g;
+    const int nt = g.nt;
+    const bool pdl = elf_use_pdl();
+    ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks * 6 * g.plane, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(int) * P.ncounters, st));
+    int seq = 0;
+    for (int sb = 0; sb < P.ns; sb += P.G) {
+        const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
+        int rc = ela_zero_fields(P, st, A_L0, A_COUNT, sb, se);
+        if (rc) return rc;
+        int lcur = 0;
+        for (int seg = P.nseg - 1; seg >= 0; --seg) {
+            const int t0 = seg * P.K, t1 = t0 + P.K < nt ? t0 + P.K : nt;
+            if (seg != P.nseg - 1) {
+                int cur = 0;
+                if (seg == 0) rc = ela_zero_state(P, st, sb, se);
+                else          rc = ela_copy_state(P, st, sb, se, P.ckpt + (size_t)(seg - 1) * P.ckpt_stride, false, 0);
+                if (rc) return rc;
+                for (int it = t0; it < t1; ++it) {
+                    rc = ela_forward_step<NN>(P, M, st, sb, se, it, true, it - t0, ea, nullptr, &seq, &cur);
+                    if (rc) return rc;
+                }
+            }
+            for (int it = t1 - 1; it >= t0; --it) {
+                if (seq + 1 > P.ncounters) return ADFWI_E_DIMS;
+                int grid;
+                ABArgs a;
+                a.w = ela_walk(P, sb, se, &grid);
+                a.w.counter = P.counters + seq++;
+                a.cp = ela_pack_ptrs(P); a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
+                a.nr = P.nr; a.rb = ela_bucket_ptrs(P);
+                for (int k = 0; k < 5; ++k) a.g[k] = g_rcv[k];
+                a.mt = ea.mt; a.sx = ea.sx; a.sz = ea.sz; a.g_src = g_src; a.gpart = P.gpart;
+                {
+                    TimedLaunch tl_(KC_EL_ADJ_FUSED, st);
+                    if (P.FS) ADFWI_CUDA(elf_launch(ela_b<NN, true>, grid, ab_smem<NN>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
+                    else      ADFWI_CUDA(elf_launch(ela_b<NN, false>, grid, ab_smem<NN>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
+                }
+                ADFWI_LAUNCH_CHECK();
+                lcur ^= 1;
+            }
+        }
+    }
+    for (int k = 0; k < 6; ++k) {
+        elf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.plane, P.nchunks, k, P.gpart, g_coef[k]);
+        ADFWI_LAUNCH_CHECK();
+    }
+    return ADFWI_OK;
+}
+
 }  // namespace
 
 bool elf_supported(const adfwi_elastic_desc* d)
@@ -2633,6 +2955,56 @@ int elf_backward(const adfwi_elastic_desc* d, const float* const* coef, const fl
     if (rc) return rc;
     EArgs ea; ea.mt = mt; ea.src_v = src_v; ea.sx = sx; ea.sz = sz;
     return P.NN == 2 ? elf_backward_t<2>(P, M, st, ea, g_rcv, g_coef, g_src) : elf_backward_t<3>(P, M, st, ea, g_rcv, g_coef, g_src);
+}
+
+
+// ---- sponge (ABL) pipeline entry points ------------------------------------------------------------
+bool ela_supported(const adfwi_elastic_desc* d)
+{
+    if (!d || d->abc_pml) return false;
+    if (d->fd_order != 4 && d->fd_order != 6) return false;
+    if (d->reserved[0] & 1) return false;
+    if (d->nzp >= 32768 || d->nxp >= 65536) return false;      // receiver cells are packed as (z<<16)|x
+    if ((uint64_t)A_COUNT * (uint64_t)d->ns >= (1ull << 31)) return false;
+    return true;
+}
+
+size_t ela_workspace_bytes(const adfwi_elastic_desc* d)
+{
+    EAPlan P;
+    ela_make_plan(d, nullptr, &P, 148);
+    return P.bytes;
+}
+
+int ela_forward(const adfwi_elastic_desc* d, const float* const* coef, const float* damp, const float* mt,
+                const float* src_v, const int64_t* sx, const int64_t* sz, const int64_t* rx, const int64_t* rz,
+                float* const* rcv, float* const* illum, void* ws, cudaStream_t st)
+{
+    EAPlan P;
+    ela_make_plan(d, ws, &P, 148);
+    int rc = P.NN == 2 ? ela_init_kernels<2>() : ela_init_kernels<3>();
+    if (rc) return rc;
+    EAMaps M;
+    rc = ela_make_maps(P, &M);
+    if (rc) return rc;
+    rc = ela_setup(P, st, coef, damp, rx, rz);
+    if (rc) return rc;
+    EArgs ea; ea.mt = mt; ea.src_v = src_v; ea.sx = sx; ea.sz = sz;
+    return P.NN == 2 ? ela_forward_t<2>(P, M, st, ea, rcv, illum) : ela_forward_t<3>(P, M, st, ea, rcv, illum);
+}
+
+int ela_backward(const adfwi_elastic_desc* d, const float* mt, const float* src_v, const int64_t* sx, const int64_t* sz,
+                 const float* const* g_rcv, float* const* g_coef, float* g_src, void* ws, cudaStream_t st)
+{
+    EAPlan P;                       // pack and receiver buckets were left in the workspace by forward
+    ela_make_plan(d, ws, &P, 148);
+    int rc = P.NN == 2 ? ela_init_kernels<2>() : ela_init_kernels<3>();
+    if (rc) return rc;
+    EAMaps M;
+    rc = ela_make_maps(P, &M);
+    if (rc) return rc;
+    EArgs ea; ea.mt = mt; ea.src_v = src_v; ea.sx = sx; ea.sz = sz;
+    return P.NN == 2 ? ela_backward_t<2>(P, M, st, ea, g_rcv, g_coef, g_src) : ela_backward_t<3>(P, M, st, ea, g_rcv, g_coef, g_src);
 }
 
 }  // namespace adfwi

@@ -12,5 +12,13 @@ int elf_forward(const adfwi_elastic_desc* d, const float* const* coef, const flo
 int elf_backward(const adfwi_elastic_desc* d, const float* const* coef, const float* bcx, const float* bcz, const float* mt,
                  const float* src_v, const int64_t* sx, const int64_t* sz, const int64_t* rx, const int64_t* rz,
                  const float* const* g_rcv, float* const* g_coef, float* g_src, void* ws, cudaStream_t st);
+// sponge (ABL) boundary: ela_f / ela_b (elastic_abl_fused.inl); damp = dense sponge plane [nzp][nxp]
+bool ela_supported(const adfwi_elastic_desc* d);
+size_t ela_workspace_bytes(const adfwi_elastic_desc* d);
+int ela_forward(const adfwi_elastic_desc* d, const float* const* coef, const float* damp, const float* mt,
+                const float* src_v, const int64_t* sx, const int64_t* sz, const int64_t* rx, const int64_t* rz,
+                float* const* rcv, float* const* illum, void* ws, cudaStream_t st);
+int ela_backward(const adfwi_elastic_desc* d, const float* mt, const float* src_v, const int64_t* sx, const int64_t* sz,
+                 const float* const* g_rcv, float* const* g_coef, float* g_src, void* ws, cudaStream_t st);
 }
 #endif

@@ -682,7 +682,10 @@ def run_b200_elastic(args, wl):
         fwd_name = "forward step, recording (elf_f)" if "el_fwd_fused" in avg else "forward step, recording (elf_s + elf_v)"
         cells = batch * nzp * nxp            # one launch advances every shot of the batch by one step
         if adj > 0 and fwd > 0:
-            if args.abc != "PML":
+            abl_fused = args.abc != "PML" and "el_fwd_fused" in avg
+            if abl_fused:
+                adj_name, fwd_name = "adjoint step (ela_b)", "forward step, recording (ela_f)"
+            elif args.abc != "PML":
                 adj_name, fwd_name = "adjoint step (generic ABL kernels)", "forward step, recording (generic ABL kernels)"
             dom_name, dom_ms, dom_bytes = ((adj_name, adj, B_adj) if adj >= fwd else (fwd_name, fwd, B_fwd))
             ach = dom_bytes * cells / (dom_ms * 1e-3) / 1e9
@@ -710,7 +713,10 @@ def run_b200_elastic(args, wl):
                                       "adjoint": B_adj * cells / (adj * 1e-3) / 1e9 / peak},
                     "per_kernel_avg_ms": avg}
         cpu_base = cpu_baseline_entry(args, wl) if args.cpu_baseline else None
-        if roof is not None and args.abc != "PML":
+        if roof is not None and args.abc != "PML" and "el_fwd_fused" in avg:
+            roof["note"] = ("sponge (ABL) boundary on the fused pair ela_f / ela_b: 5 unsplit fields, forward 84 B (64 + 20 recording), adjoint 84 B per "
+                            "cell-update; the checkpointed row adds one plain forward sweep (64 B)")
+        elif roof is not None and args.abc != "PML":
             # the generic kernels advance the library's own shot groups, not the whole batch, per launch: only the
             # whole-gradient fraction is meaningful here
             w = roof["whole_step_frac"]
