@@ -53,6 +53,8 @@ SYMBOLS = [
     "adfwi_acoustic_workspace_bytes", "adfwi_acoustic_group_size", "adfwi_acoustic_forward", "adfwi_acoustic_backward",
     "adfwi_elastic_workspace_bytes", "adfwi_elastic_forward", "adfwi_elastic_backward",
     "adfwi_gradproc_workspace_bytes", "adfwi_gradproc_forward", "adfwi_gradproc_smooth2d",
+    "adfwi_misfit_workspace_bytes", "adfwi_misfit_forward", "adfwi_misfit_adjoint_source",
+    "adfwi_regularization_workspace_bytes", "adfwi_regularization_forward", "adfwi_regularization_backward",
     "adfwi_strerror", "adfwi_abi_version", "adfwi_launch_count",
     "adfwi_timing_enable", "adfwi_timing_collect",
 ]
@@ -73,8 +75,33 @@ class GradProcDesc(C.Structure):
                 ("thred", C.c_double), ("vmax", C.c_double)]
 
 
+class MisfitDesc(C.Structure):
+    """adfwi_misfit_desc of include/adfwi_b200.h"""
+    _fields_ = [("ns", C.c_int32), ("nt", C.c_int32), ("nr", C.c_int32), ("kind", C.c_int32), ("normalize", C.c_int32),
+                ("reserved", C.c_int32 * 3), ("dt", C.c_double)]
+
+
+class RegularizationDesc(C.Structure):
+    """adfwi_regularization_desc of include/adfwi_b200.h"""
+    _fields_ = [("nz", C.c_int32), ("nx", C.c_int32), ("kind", C.c_int32), ("reserved", C.c_int32),
+                ("dx", C.c_double), ("dz", C.c_double), ("alphax", C.c_double), ("alphaz", C.c_double)]
+
+
 def bind(lib):
     vp = C.c_void_p
+    if hasattr(lib, "adfwi_misfit_forward"):         # absent from the host-emulation fixture of tests/emul
+        lib.adfwi_misfit_workspace_bytes.restype = C.c_size_t
+        lib.adfwi_misfit_workspace_bytes.argtypes = [C.POINTER(MisfitDesc)]
+        lib.adfwi_misfit_forward.restype = C.c_int
+        lib.adfwi_misfit_forward.argtypes = [C.POINTER(MisfitDesc), vp, vp, vp, vp, C.c_size_t, vp]
+        lib.adfwi_misfit_adjoint_source.restype = C.c_int
+        lib.adfwi_misfit_adjoint_source.argtypes = [C.POINTER(MisfitDesc), vp, vp, vp, vp, vp, C.c_size_t, vp]
+        lib.adfwi_regularization_workspace_bytes.restype = C.c_size_t
+        lib.adfwi_regularization_workspace_bytes.argtypes = [C.POINTER(RegularizationDesc)]
+        lib.adfwi_regularization_forward.restype = C.c_int
+        lib.adfwi_regularization_forward.argtypes = [C.POINTER(RegularizationDesc), vp, vp, vp, C.c_size_t, vp]
+        lib.adfwi_regularization_backward.restype = C.c_int
+        lib.adfwi_regularization_backward.argtypes = [C.POINTER(RegularizationDesc), vp, vp, vp, vp, C.c_size_t, vp]
     if hasattr(lib, "adfwi_gradproc_forward"):      # absent from the host-emulation fixture of tests/emul
         lib.adfwi_gradproc_workspace_bytes.restype = C.c_size_t
         lib.adfwi_gradproc_workspace_bytes.argtypes = [C.POINTER(GradProcDesc)]

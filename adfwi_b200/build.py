@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libadfwi_b200.so")
-SOURCES = ["api.cu", "acoustic.cu", "acoustic_fused.cu", "elastic.cu", "elastic_fused.cu", "gradproc.cu"]
+SOURCES = ["api.cu", "acoustic.cu", "acoustic_fused.cu", "elastic.cu", "elastic_fused.cu", "gradproc.cu", "objective.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC,-O2", "-shared",
@@ -33,7 +33,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inl"))]
     deps.append(os.path.join(HERE, "..", "include", "adfwi_b200.h"))
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)

@@ -185,6 +185,54 @@ int adfwi_gradproc_forward(const adfwi_gradproc_desc* desc, const float* grad, c
 /* smooth2d alone (gradient_process.py:30-49) on a float64 plane; workspace as above with nz, nx set */
 int adfwi_gradproc_smooth2d(int nz, int nx, int span, const double* in, double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Record post-processing.  Replaces, for one shot batch, the per-trace max-abs
+ * normalisation of the synthetic records (ADFWI/fwi/acoustic_fwi.py:149-150: syn / max_t |syn|, keepdim over
+ * time; elastic_fwi.py:224-255) followed by the misfit and by what autograd derives from both:
+ *   kind 0  Misfit_waveform_L2.forward         (ADFWI/fwi/misfit/L2.py:22-28):   sum_traces sqrt(sum_t (obs - syn)^2 dt)
+ *   kind 1  Misfit_global_correlation.forward  (ADFWI/fwi/misfit/GlobalCorrelation.py:43-70)
+ * syn, obs: [ns][nt][nr] float32 (obs already normalised by the caller, as the reference does once at
+ * construction, acoustic_fwi.py:68-70).  forward() writes the scalar loss (device float) and leaves the
+ * per-trace coefficients of the adjoint source in the workspace; adjoint_source() writes
+ * g_syn = grad_loss * d(loss)/d(syn) [ns][nt][nr] (grad_loss: device float, NULL = 1).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t ns, nt, nr;
+    int32_t kind;             /* 0 = L2 waveform, 1 = global correlation */
+    int32_t normalize;        /* 1 = per-trace max-abs normalisation of syn first */
+    int32_t reserved[3];
+    double  dt;               /* the misfit's dt (the examples pass 1 or the sampling interval) */
+} adfwi_misfit_desc;
+
+size_t adfwi_misfit_workspace_bytes(const adfwi_misfit_desc* desc);
+int adfwi_misfit_forward(const adfwi_misfit_desc* desc, const float* syn, const float* obs, float* loss,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int adfwi_misfit_adjoint_source(const adfwi_misfit_desc* desc, const float* syn, const float* obs, const float* grad_loss,
+                                float* g_syn, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model regularisers.  Replaces Regularization.forward of
+ *   kind 0  TV_1order        (ADFWI/fwi/regularization/tv_1order.py:25-52)
+ *   kind 1  Tikhonov_1order  (tikhonov_1order.py:22-52)
+ *   kind 2  TV_2order        (tv_2order.py:25-52)
+ *   kind 3  Tikhonov_2order  (tikhonov_2order.py:26-55)
+ * and its autograd derivative.  m: [nz][nx] float32; dx, dz in metres (the reference converts to km);
+ * alphax, alphaz: the factors AFTER the caller's step decay (regular_StepLR, base.py:16-18).
+ * forward() writes the scalar value (device float) and keeps what backward() needs in the workspace.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t nz, nx;
+    int32_t kind;
+    int32_t reserved;
+    double  dx, dz, alphax, alphaz;
+} adfwi_regularization_desc;
+
+size_t adfwi_regularization_workspace_bytes(const adfwi_regularization_desc* desc);
+int adfwi_regularization_forward(const adfwi_regularization_desc* desc, const float* m, float* value,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int adfwi_regularization_backward(const adfwi_regularization_desc* desc, const float* m, const float* grad_value, float* g_m,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* misc */
 const char* adfwi_strerror(int code);
 int adfwi_abi_version(void);

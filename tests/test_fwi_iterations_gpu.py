@@ -15,7 +15,8 @@ def rel_l2(a, b):
 
 
 def test_three_fwi_iterations_match_reference(golden_dir):
-    from adfwi_b200 import fwi, synthetic as syn
+    import fwi_loops as fwi
+    from adfwi_b200 import synthetic as syn
     from adfwi_b200.propagator import AcousticPropagator, GradProcessor
     g = np.load(f"{golden_dir}/fwi_acoustic_3iter.npz")
     dev = torch.device("cuda:0")
@@ -46,7 +47,8 @@ def test_two_elastic_fwi_iterations_match_reference(golden_dir):
     """Same at the elastic level: ElasticFWI.forward of the unmodified reference (vx + vz misfit, vp / vs / rho updated,
     gradient processor per parameter, SGD + StepLR; tests/golden/make_golden_fwi_elastic.py) against the device loop
     through ElasticPropagator (fused split-PML kernels) and the torch parameterisation."""
-    from adfwi_b200 import fwi, synthetic as syn
+    import fwi_loops as fwi
+    from adfwi_b200 import synthetic as syn
     from adfwi_b200.propagator import ElasticPropagator, GradProcessor
     g = np.load(f"{golden_dir}/fwi_elastic_2iter.npz")
     dev = torch.device("cuda:0")
