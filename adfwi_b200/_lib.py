@@ -63,7 +63,7 @@ SYMBOLS = [
 KERNEL_CLASSES = [
     "ac_fwd_p", "ac_fwd_uw", "ac_record", "ac_adj_inject", "ac_adj_a", "ac_adj_b",
     "el_fwd_stress", "el_fwd_vel", "el_record", "el_adj_inject", "el_adj_vel", "el_adj_stress",
-    "ac_fwd_fused", "ac_adj_fused", "other", "el_fwd_fused", "el_adj_fused",
+    "ac_fwd_fused", "ac_adj_fused", "other", "el_fwd_fused", "el_adj_fused", "ac_fwd_persist", "ac_adj_persist",
 ]
 
 

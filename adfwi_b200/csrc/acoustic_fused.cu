@@ -36,6 +36,7 @@
 #include "tma.cuh"
 #include "acoustic_fused.h"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace adfwi {
 
@@ -1035,6 +1036,125 @@ int acf_forward_step(const FPlan& P, const StepMaps& M, cudaStream_t st, int cur
     return ADFWI_OK;
 }
 
+
+#include "acoustic_persist.inl"
+
+// ---- cluster-persistent small-grid path: host side ------------------------------------------------------------------
+constexpr int PP_SMEM_MAX = 227 * 1024 - 1024;      // dynamic shared memory one CTA may take (1 KB left to the system)
+
+inline bool acf_use_persist()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_PERSIST"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
+struct PPlan { PGeom g; int kmax; size_t smem_fwd, smem_adj; };
+
+template <bool FS, int KMAX> int pp_set_attrs()
+{
+    int rc = (int)cudaFuncSetAttribute(acp_fwd<FS, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_MAX);
+    rc |= (int)cudaFuncSetAttribute(acp_adj<FS, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_MAX);
+    return rc;
+}
+int pp_init_kernels()
+{
+    static bool done_dev[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (done_dev[dev]) return 0;
+    int rc = 0;
+#define PPK(K) rc |= pp_set_attrs<true, K>(); rc |= pp_set_attrs<false, K>();
+    PPK(1) PPK(2) PPK(3) PPK(4) PPK(6) PPK(8)
+#undef PPK
+    if (!rc) done_dev[dev] = true;
+    return rc;
+}
+inline int pp_round_kmax(int k) { return k <= 4 ? k : (k <= 6 ? 6 : 8); }
+
+// co-resident clusters of `nc` CTAs with `smem` bytes each on the current device (0 = cannot launch); the driver query costs
+// milliseconds, so its answers are cached per (device, cluster size, shared-memory size)
+template <typename Kern> int pp_max_clusters_query(Kern kern, int nc, size_t smem);
+template <typename Kern> int pp_max_clusters(Kern kern, int nc, size_t smem)
+{
+    struct Ent { int dev, nc; size_t smem; int n; };
+    static Ent cache[64]; static int ncache = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < ncache; ++i) if (cache[i].dev == dev && cache[i].nc == nc && cache[i].smem == smem) return cache[i].n;
+    const int n = pp_max_clusters_query(kern, nc, smem);
+    if (ncache < 64) { cache[ncache].dev = dev; cache[ncache].nc = nc; cache[ncache].smem = smem; cache[ncache].n = n; ++ncache; }
+    return n;
+}
+template <typename Kern> int pp_max_clusters_query(Kern kern, int nc, size_t smem)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nc * 64); cfg.blockDim = dim3(PNT); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// Is the problem small enough for the persistent path, and with which decomposition?  One cluster per shot, z strips of R rows.
+bool pp_make_plan(const adfwi_acoustic_desc* d, const FPlan& P, PPlan* Q)
+{
+    if (!acf_use_persist() || (d->reserved[0] & 2)) return false;
+    if (P.need_g2) return false;                              // the density gradient stays on the per-step kernels
+    if (P.save && P.K < P.g.nt) return false;                 // store-all only (small grids: the history fits)
+    const FGeom& f = P.g;
+    const int nrows = f.nzp - f.zlo;
+    const int nxg = cdiv(f.nxp, 4);
+    const int pitch = 4 * nxg + 2 * PXPAD;
+    if (pp_init_kernels()) return false;
+    double best = 1e30; int best_nc = 0;
+    static const int force_nc = getenv("ADFWI_B200_PERSIST_NC") ? atoi(getenv("ADFWI_B200_PERSIST_NC")) : 0;     // tuning / A-B switch
+    static const bool debug = getenv("ADFWI_B200_DEBUG") != nullptr;
+    for (int nc = 1; nc <= 8; ++nc) {
+        const int R = cdiv(nrows, nc);
+        if (R < 4) break;
+        if (force_nc && nc != force_nc) continue;
+        const size_t sm_f = pp_smem_floats(R, pitch, 3, 0) * 4, sm_a = pp_smem_floats(R, pitch, 2, 2) * 4;
+        if (sm_f > (size_t)PP_SMEM_MAX || sm_a > (size_t)PP_SMEM_MAX) continue;
+        const int kraw = cdiv(R * nxg, PNT);
+        if (kraw > 8) continue;
+        const int ncl = P.FS ? pp_max_clusters(acp_adj<true, 1>, nc, sm_a) : pp_max_clusters(acp_adj<false, 1>, nc, sm_a);
+        if (ncl < 1) continue;
+        // cost model: waves x (two cluster barriers + halo pulls ~ 0.6 us, ~0.2 us per float4 group a thread owns)
+        const double cost = (double)cdiv(P.ns, ncl) * (0.6 + 0.2 * kraw);
+        if (debug) fprintf(stderr, "adfwi_b200: persistent plan candidate NC=%d R=%d groups/thread=%d co-resident clusters=%d smem=%zu cost=%.2f\n", nc, R, kraw, ncl, sm_a, cost);
+        if (cost < best) { best = cost; best_nc = nc; }
+    }
+    if (!best_nc) return false;
+    PGeom& g = Q->g;
+    g.nzp = f.nzp; g.nxp = f.nxp; g.ld = f.ld; g.fs = f.fs; g.zlo = f.zlo; g.nt = f.nt; g.nabc = f.nabc;
+    g.NC = best_nc; g.R = cdiv(nrows, best_nc); g.nxg = nxg; g.pitch = pitch; g.cpld = f.cpld; g.plane = f.plane;
+    g.c1 = f.c1; g.c2 = f.c2; g.dt = f.dt;
+    Q->kmax = pp_round_kmax(cdiv(g.R * nxg, PNT));
+    Q->smem_fwd = pp_smem_floats(g.R, pitch, 3, 0) * 4; Q->smem_adj = pp_smem_floats(g.R, pitch, 2, 2) * 4;
+    return true;
+}
+
+template <typename Kern, typename Args>
+cudaError_t pp_launch_k(Kern kern, int nshots, const PGeom& g, size_t smem, cudaStream_t st, const Args& a)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nshots * g.NC); cfg.blockDim = dim3(PNT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = g.NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, g, a);
+}
+#define PP_DISPATCH(KERN, FSv, kmax, ...)                                                            \
+    ((kmax) == 1 ? pp_launch_k(KERN<FSv, 1>, __VA_ARGS__) : (kmax) == 2 ? pp_launch_k(KERN<FSv, 2>, __VA_ARGS__) : \
+     (kmax) == 3 ? pp_launch_k(KERN<FSv, 3>, __VA_ARGS__) : (kmax) == 4 ? pp_launch_k(KERN<FSv, 4>, __VA_ARGS__) : \
+     (kmax) == 6 ? pp_launch_k(KERN<FSv, 6>, __VA_ARGS__) : pp_launch_k(KERN<FSv, 8>, __VA_ARGS__))
+
 // function attributes are per device: the >48 KB dynamic shared-memory opt-in is made once per device ordinal
 int acf_init_kernels()
 {
@@ -1095,6 +1215,28 @@ int acf_forward(const adfwi_acoustic_desc* d, const float* const* coef, const fl
         ADFWI_CUDA(cudaMemsetAsync(P.ill_u, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
         ADFWI_CUDA(cudaMemsetAsync(P.ill_w, 0, sizeof(float) * g.plane, st));
     }
+    PPlan Q;
+    if (pp_make_plan(d, P, &Q)) {
+        // small grid: the whole time loop of every shot in ONE launch, state resident in the shared memory of a cluster per shot
+        PFwdArgs a;
+        a.cp = acf_pack_ptrs(P); a.src_v = src_v; a.sx = sx; a.sz = sz; a.hist = P.hist; a.hist_len = P.K;
+        a.nr = P.nr > 0 && rcv_p ? P.nr : 0; a.rx = rx; a.rz = rz; a.rcv_p = rcv_p; a.rcv_u = rcv_u; a.rcv_w = rcv_w;
+        a.ill_p = P.ill_p; a.ill_u = P.ill_u; a.ill_w = P.ill_w; a.illum = illum ? 1 : 0; a.last_chunk_start = last_chunk_start;
+        a.s_begin = 0; a.save = P.save;
+        {
+            TimedLaunch tl_(KC_AC_FWD_PERSIST, st);
+            if (P.FS) ADFWI_CUDA(PP_DISPATCH(acp_fwd, true, Q.kmax, P.ns, Q.g, Q.smem_fwd, st, a));
+            else      ADFWI_CUDA(PP_DISPATCH(acp_fwd, false, Q.kmax, P.ns, Q.g, Q.smem_fwd, st, a));
+        }
+        ADFWI_LAUNCH_CHECK();
+        if (illum) {
+            const int nx = g.nxp - 2 * g.nabc, nz = g.nzp - 2 * g.nabc;
+            acf_illum_finalize<<<dim3(cdiv(nx, 128), nz), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.nabc, P.nchunks, g.plane, P.ill_p, P.ill_u, P.ill_w,
+                                                                         illum_p, illum_u, illum_w);
+            ADFWI_LAUNCH_CHECK();
+        }
+        return ADFWI_OK;
+    }
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
         const size_t off = (size_t)sb * g.plane, cnt = (size_t)(se - sb) * g.plane * sizeof(float);
@@ -1131,7 +1273,6 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
                  const int64_t* rx, const int64_t* rz, const float* gp, const float* gu, const float* gw,
                  float* g_alpha1, float* g_alpha2, float* g_src, void* ws, cudaStream_t st)
 {
-    (void)rx; (void)rz;
     FPlan P;
     acf_make_plan(d, ws, &P, 148);
     const FGeom& g = P.g;
@@ -1144,6 +1285,22 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
     const int nt = g.nt;
     ADFWI_CUDA(cudaMemsetAsync(P.g1part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
     if (P.need_g2) ADFWI_CUDA(cudaMemsetAsync(P.g2part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
+    PPlan Q;
+    if (pp_make_plan(d, P, &Q)) {
+        PAdjArgs a;
+        a.cp = acf_pack_ptrs(P); a.sx = sx; a.sz = sz; a.hist = P.hist; a.hist_len = P.K;
+        a.nr = P.nr; a.rx = rx; a.rz = rz; a.gp = gp; a.gu = gu; a.gw = gw;
+        a.g1part = P.g1part; a.g_src = g_src; a.s_begin = 0;
+        {
+            TimedLaunch tl_(KC_AC_ADJ_PERSIST, st);
+            if (P.FS) ADFWI_CUDA(PP_DISPATCH(acp_adj, true, Q.kmax, P.ns, Q.g, Q.smem_adj, st, a));
+            else      ADFWI_CUDA(PP_DISPATCH(acp_adj, false, Q.kmax, P.ns, Q.g, Q.smem_adj, st, a));
+        }
+        ADFWI_LAUNCH_CHECK();
+        acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g1part, g_alpha1);
+        ADFWI_LAUNCH_CHECK();
+        return ADFWI_OK;
+    }
     for (int sb = 0; sb < P.ns; sb += P.G) {
         const int se = sb + P.G < P.ns ? sb + P.G : P.ns;
         const size_t off = (size_t)sb * g.plane, cnt = (size_t)(se - sb) * g.plane * sizeof(float);

@@ -20,7 +20,9 @@ TimedLaunch::TimedLaunch(int cls, cudaStream_t s) : slot(-1), st(s)
 {
     if (g_every <= 0) return;
     std::lock_guard<std::mutex> lk(g_tm);
-    if ((g_seen[cls]++ % (uint64_t)g_every) != 0 || g_samples.size() >= kMaxSamples) return;
+    // the cluster-persistent kernels run a whole sweep per launch: sample every one of them
+    const uint64_t every = (cls == KC_AC_FWD_PERSIST || cls == KC_AC_ADJ_PERSIST) ? 1 : (uint64_t)g_every;
+    if ((g_seen[cls]++ % every) != 0 || g_samples.size() >= kMaxSamples) return;
     Sample sm; sm.cls = cls;
     if (cudaEventCreate(&sm.a) != cudaSuccess || cudaEventCreate(&sm.b) != cudaSuccess) return;
     cudaEventRecord(sm.a, st);

@@ -42,7 +42,7 @@ struct Carver {
 enum KernelClass {
     KC_AC_FWD_P = 0, KC_AC_FWD_UW, KC_AC_RECORD, KC_AC_ADJ_INJECT, KC_AC_ADJ_A, KC_AC_ADJ_B,
     KC_EL_FWD_STRESS, KC_EL_FWD_VEL, KC_EL_RECORD, KC_EL_ADJ_INJECT, KC_EL_ADJ_VEL, KC_EL_ADJ_STRESS,
-    KC_AC_FWD_FUSED, KC_AC_ADJ_FUSED, KC_OTHER, KC_EL_FWD_FUSED, KC_EL_ADJ_FUSED, KC_COUNT
+    KC_AC_FWD_FUSED, KC_AC_ADJ_FUSED, KC_OTHER, KC_EL_FWD_FUSED, KC_EL_ADJ_FUSED, KC_AC_FWD_PERSIST, KC_AC_ADJ_PERSIST, KC_COUNT
 };
 #ifdef ADFWI_HOST_EMUL
 struct TimedLaunch { TimedLaunch(int, cudaStream_t) {} };

@@ -33,6 +33,9 @@ config = {
     # True: run the generic one-cell-per-thread kernels instead of the fused TMA pipeline
     # (cross-checks in the tests; the density gradient always uses the generic kernels)
     "force_generic": os.environ.get("ADFWI_B200_GENERIC", "0") == "1",
+    # False: never take the cluster-persistent small-grid kernels (whole time loop in one launch, state resident in shared
+    # memory); they are used automatically when the active region fits and the history is store-all
+    "persistent": os.environ.get("ADFWI_B200_PERSIST", "1") != "0",
 }
 
 
@@ -100,7 +103,7 @@ class AcousticFD(torch.autograd.Function):
         save = need[0] or need[1] or need[5]
         desc = make_desc(nzp, nxp, ns, nt, nr, nabc, free_surface, dt, n_segments, save,
                          0, need[1], config["shots_per_group"])
-        desc.reserved[0] = 1 if config["force_generic"] else 0
+        desc.reserved[0] = (1 if config["force_generic"] else 0) | (0 if config.get("persistent", True) else 2)
         desc.reserved[1] = int(config.get("shots_per_chunk", 0))
         with torch.cuda.device(dev):
             if save:

@@ -73,7 +73,7 @@ def _run_vp_only(g, comp, **cfg):
 @pytest.mark.parametrize("name", ["acoustic_fs", "acoustic_nofs"])
 @pytest.mark.parametrize("cfg", [dict(), dict(ckpt_interval=40, shots_per_group=1), dict(ckpt_interval=64),
                                  dict(force_generic=True), dict(shots_per_chunk=2), dict(shots_per_chunk=3, shots_per_group=3),
-                                 dict(shots_per_chunk=8, ckpt_interval=50)])
+                                 dict(shots_per_chunk=8, ckpt_interval=50), dict(persistent=False), dict(persistent=False, shots_per_chunk=1)])
 def test_fused_pipeline_vp_only(golden_dir, name, cfg):
     """vp-only gradients take the fused TMA pipeline (the default fast path); force_generic
     cross-checks the generic kernels on the same inputs."""
@@ -168,3 +168,41 @@ def test_second_device_in_the_same_process(golden_dir):
         sum((rec[k] * t("W_" + k)).sum() for k in ("vx", "vz")).backward()
         assert np.array_equal(rec["vz"].detach().cpu().numpy(), ge["rec_vz"]), dev
         assert rel_l2(L["C11"].grad.cpu().numpy(), ge["g_C11_vel"]) <= 2e-5, dev
+
+
+@pytest.mark.parametrize("fs", [True, False])
+@pytest.mark.parametrize("shape", [(83, 149, 12), (40, 300, 8), (88, 200, 30)])
+def test_persistent_small_grid_matches_per_step_kernels(fs, shape):
+    """Cluster-persistent kernels (acp_fwd / acp_adj: one launch per sweep, z strips over a cluster, DSMEM halo pulls) against the
+    per-step TMA kernels on grids that split into 2..8 strips: records bit-identical, illumination, vp gradient and source gradient."""
+    from adfwi_b200.propagator import acoustic_kernels as ak
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    nz, nx, nabc = shape
+    nt, ns = 140, 6
+    v = (1800 + 1500 * torch.rand(nz, nx, device=dev))
+    rho = 2000 + 200 * torch.rand(nz, nx, device=dev)
+    damp = 30 * torch.rand(nz + 2 * nabc, nx + 2 * nabc, device=dev)
+    sx = torch.tensor([3, nx // 2, nx - 2, 17, 18, nx // 3], device=dev); sz = torch.tensor([0, nz // 2, 2, nz - 1, 1, nz // 3], device=dev)
+    rx = torch.cat([torch.arange(0, nx, 2), torch.tensor([5, 5])]).to(dev)
+    rz = torch.cat([torch.zeros(len(range(0, nx, 4)), dtype=torch.long), torch.full((len(range(0, nx, 2)) - len(range(0, nx, 4)),), nz // 2),
+                    torch.tensor([nz - 1, nz - 1])]).to(dev)
+    src = torch.randn(ns, nt, device=dev)
+    W = torch.randn(ns, nt, rx.numel(), device=dev)
+    out = {}
+    for mode in (True, False):
+        old = dict(ak.config); ak.config.update(persistent=mode)
+        try:
+            vv = v.clone().requires_grad_(True)
+            ss = src.clone().requires_grad_(True)
+            rec = ak.forward_kernel(nx, nz, 10.0, 10.0, nt, 1e-3, nabc, fs, sx, sz, ns, ss, rx, rz, rx.numel(), damp, vv, rho, checkpoint_segments=2, device=dev)
+            ((rec["p"] * W).sum() + 1e6 * (rec["u"] * W).sum() + 1e6 * (rec["w"] * W).sum()).backward()
+            out[mode] = (rec, vv.grad.clone(), ss.grad.clone())
+        finally:
+            ak.config.clear(); ak.config.update(old)
+    for k in ("p", "u", "w"):
+        assert torch.equal(out[True][0][k], out[False][0][k]), (fs, shape, k)
+    for k in ("forward_wavefield_p", "forward_wavefield_u", "forward_wavefield_w"):
+        assert rel_l2(out[True][0][k].cpu().numpy(), out[False][0][k].cpu().numpy()) < 1e-5, k
+    assert rel_l2(out[True][1].cpu().numpy(), out[False][1].cpu().numpy()) < 1e-5
+    assert rel_l2(out[True][2].cpu().numpy(), out[False][2].cpu().numpy()) < 1e-5
