@@ -1054,7 +1054,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
 }
 
 template <int NN, bool FS, bool SAVE>
-__global__ void __launch_bounds__(NTH, 2)
+__global__ void __launch_bounds__(NTH, NN == 2 ? 2 : 1)      // O(2,6): one CTA per SM (shared memory) -> the full register file per thread
 elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap th2, const EGeom g, const FArgs a)
 {
     using G = Geo<NN>;
@@ -1995,7 +1995,7 @@ __device__ __forceinline__ void b_tile(const CUtensorMap* th, const CUtensorMap*
 }
 
 template <int NN, bool FS>
-__global__ void __launch_bounds__(NTH, 2)
+__global__ void __launch_bounds__(NTH, NN == 2 ? 2 : 1)      // O(2,6): one CTA per SM (shared memory) -> the full register file per thread
 elf_b(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMap th2, const __grid_constant__ CUtensorMap thh, const EGeom g, const BArgs a)
 {
     static_assert(RPT == 1, "elf_b: one float4 group per thread");
@@ -2342,8 +2342,8 @@ template <int NN> constexpr int k1_smem() { return NSTAGE * Geo<NN>::K1_STAGE + 
 template <int NN> constexpr int k2_smem() { return NSTAGE * Geo<NN>::K2_STAGE + TAIL_SMALL; }
 template <int NN> constexpr int b_smem() { return GeoB<NN>::SMEM + TAIL_SMALL + 2 * (int)sizeof(Cursor); }
 static_assert(2 * (s_smem<3>() + 1024) <= 233472 && 2 * (k2_smem<3>() + 1024) <= 233472 && 2 * (f_smem<2>() + 1024) <= 233472 && f_smem<3>() <= 232448 &&
-              2 * (b_smem<2>() + 1024) <= 233472,
-              "two CTAs per SM must fit in shared memory (the O(2,6) fused forward kernel runs one CTA per SM)");
+              2 * (b_smem<2>() + 1024) <= 233472 && b_smem<3>() <= 232448,
+              "two CTAs per SM must fit in shared memory (the O(2,6) fused forward and reverse kernels run one CTA per SM)");
 
 // function attributes are per device: the >48 KB dynamic shared-memory opt-in is made once per device ordinal
 template <int NN> int elf_init_kernels()
@@ -2363,7 +2363,7 @@ template <int NN> int elf_init_kernels()
     rc |= elf_set_smem(elf_f<NN, false, true>, f_smem<NN>());  rc |= elf_set_smem(elf_f<NN, false, false>, f_smem<NN>());
     rc |= elf_set_smem(elf_k1<NN, true>, k1_smem<NN>());       rc |= elf_set_smem(elf_k1<NN, false>, k1_smem<NN>());
     rc |= elf_set_smem(elf_k2<NN, true>, k2_smem<NN>());       rc |= elf_set_smem(elf_k2<NN, false>, k2_smem<NN>());
-    if (NN == 2) { rc |= elf_set_smem(elf_b<2, true>, b_smem<2>()); rc |= elf_set_smem(elf_b<2, false>, b_smem<2>()); }
+    rc |= elf_set_smem(elf_b<NN, true>, b_smem<NN>()); rc |= elf_set_smem(elf_b<NN, false>, b_smem<NN>());
     if (!rc) done = true;
     return rc;
 }
@@ -2379,12 +2379,14 @@ inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid)
 
 struct EArgs { const float *mt, *src_v; const int64_t *sx, *sz; };
 
-// reverse step: the fused kernel elf_b (O(2,4) only) unless ADFWI_B200_EL_ADJ_SPLIT=1 selects the two-launch form elf_k1 + elf_k2
-inline bool elf_split_adjoint()
+// reverse step: the fused kernel elf_b for O(2,4), the two-launch form elf_k1 + elf_k2 for O(2,6); ADFWI_B200_EL_ADJ_SPLIT=1 / =0 force either
+// O(2,6): the fused kernel fits one CTA per SM only (139 KB of shared memory) and measured 0.376 ms per launch against 0.334 ms for the
+// pair on the C3 grid (profiles/r02e_o26_reverse.md), so the pair stays the default there; ADFWI_B200_EL_ADJ_SPLIT=0 selects elf_b<3>.
+inline bool elf_split_adjoint(int NN)
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ADFWI_B200_EL_ADJ_SPLIT"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v != 0;
+    if (v < 0) { const char* e = getenv("ADFWI_B200_EL_ADJ_SPLIT"); v = !e ? 2 : (e[0] == '1' ? 1 : 0); }
+    return v == 2 ? NN == 3 : v == 1;
 }
 
 inline bool elf_split_forward()
@@ -2537,7 +2539,7 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                 }
             }
             for (int it = t1 - 1; it >= t0; --it) {
-                if (NN == 2 && !elf_split_adjoint()) {
+                if (!elf_split_adjoint(NN)) {
                     BArgs a;
                     a.cp = elf_pack_ptrs(P); a.tflags = P.tflags; a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
                     a.nr = P.nr; a.rb = elf_bucket_ptrs(P);
@@ -2547,8 +2549,8 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
                     a.gpart = P.gpart; a.w = w; a.w.counter = P.counters + seq++;
                     {
                         TimedLaunch tl_(KC_EL_ADJ_FUSED, st);
-                        if (P.FS) ADFWI_CUDA(elf_launch(elf_b<2, true>, grid, b_smem<2>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
-                        else      ADFWI_CUDA(elf_launch(elf_b<2, false>, grid, b_smem<2>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
+                        if (P.FS) ADFWI_CUDA(elf_launch(elf_b<NN, true>, grid, b_smem<NN>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
+                        else      ADFWI_CUDA(elf_launch(elf_b<NN, false>, grid, b_smem<NN>(), st, pdl, M.halo, M.halo2, M.hist, g, a));
                     }
                     ADFWI_LAUNCH_CHECK();
                     lcur ^= 1;

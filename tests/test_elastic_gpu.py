@@ -184,10 +184,10 @@ def test_fused_large_grid_matches_generic(order, shape):
             assert e < 2e-5, (order, fs, k, e)
 
 
-@pytest.mark.parametrize("switch", ["ADFWI_B200_EL_ADJ_SPLIT=1", "ADFWI_B200_EL_LEAN=0", "ADFWI_B200_EL_SPLIT=1"])
+@pytest.mark.parametrize("switch", ["ADFWI_B200_EL_ADJ_SPLIT=1", "ADFWI_B200_EL_LEAN=0", "ADFWI_B200_EL_SPLIT=1", "ADFWI_B200_EL_ADJ_SPLIT=0"])
 def test_kernel_variant_switches(golden_dir, switch):
     """The A/B switches of the split-PML pipeline keep working: EL_ADJ_SPLIT=1 = reverse step as the pair elf_k1 + elf_k2
-    (what O(2,6) always runs), EL_LEAN=0 = full split treatment on damping-free tiles (8 history planes, both halves
+    (the default of O(2,6)), EL_ADJ_SPLIT=0 = the fused reverse kernel also for O(2,6) (elf_b<3>, one CTA per SM), EL_LEAN=0 = full split treatment on damping-free tiles (8 history planes, both halves
     of every pair staged), EL_SPLIT=1 = forward step as elf_s + elf_v.  The switches are read once per process, so the
     golden and large-grid checks run in a child process."""
     import os
@@ -196,7 +196,8 @@ def test_kernel_variant_switches(golden_dir, switch):
     k, v = switch.split("=")
     env = dict(os.environ, **{k: v})
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                        "(test_golden_records_and_gradients and pml_o4 and cfg0) or (fused_large and shape1-4)"], env=env,
+                        "(test_golden_records_and_gradients and pml_o4 and cfg0) or (fused_large and shape1-4)" if v != "0" else
+                        "(test_golden_records_and_gradients and pml_o6 and cfg0) or (fused_large and not abl and shape1-6)"], env=env,
                        capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
