@@ -55,6 +55,7 @@ SYMBOLS = [
     "adfwi_gradproc_workspace_bytes", "adfwi_gradproc_forward", "adfwi_gradproc_smooth2d",
     "adfwi_misfit_workspace_bytes", "adfwi_misfit_forward", "adfwi_misfit_adjoint_source",
     "adfwi_regularization_workspace_bytes", "adfwi_regularization_forward", "adfwi_regularization_backward",
+    "adfwi_elastic_moduli_forward", "adfwi_elastic_moduli_backward", "adfwi_elastic_pad_forward", "adfwi_elastic_pad_backward",
     "adfwi_strerror", "adfwi_abi_version", "adfwi_launch_count",
     "adfwi_timing_enable", "adfwi_timing_collect",
 ]
@@ -87,8 +88,28 @@ class RegularizationDesc(C.Structure):
                 ("dx", C.c_double), ("dz", C.c_double), ("alphax", C.c_double), ("alphaz", C.c_double)]
 
 
+class ModuliDesc(C.Structure):
+    """adfwi_elastic_moduli_desc of include/adfwi_b200.h"""
+    _fields_ = [("nz", C.c_int32), ("nx", C.c_int32), ("hti", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PadDesc(C.Structure):
+    """adfwi_elastic_pad_desc of include/adfwi_b200.h"""
+    _fields_ = [("nz", C.c_int32), ("nx", C.c_int32), ("nzp", C.c_int32), ("nxp", C.c_int32), ("pml", C.c_int32), ("top", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
 def bind(lib):
     vp = C.c_void_p
+    if hasattr(lib, "adfwi_elastic_moduli_forward"):
+        lib.adfwi_elastic_moduli_forward.restype = C.c_int
+        lib.adfwi_elastic_moduli_forward.argtypes = [C.POINTER(ModuliDesc), vp, vp, vp, vp, vp, C.POINTER(PtrArray6), vp]
+        lib.adfwi_elastic_moduli_backward.restype = C.c_int
+        lib.adfwi_elastic_moduli_backward.argtypes = [C.POINTER(ModuliDesc), vp, vp, vp, vp, vp, C.POINTER(PtrArray6), vp, vp, vp, vp, vp, vp]
+        lib.adfwi_elastic_pad_forward.restype = C.c_int
+        lib.adfwi_elastic_pad_forward.argtypes = [C.POINTER(PadDesc), C.POINTER(PtrArray6), C.POINTER(PtrArray6), vp]
+        lib.adfwi_elastic_pad_backward.restype = C.c_int
+        lib.adfwi_elastic_pad_backward.argtypes = [C.POINTER(PadDesc), C.POINTER(PtrArray6), C.POINTER(PtrArray6), vp]
     if hasattr(lib, "adfwi_misfit_forward"):         # absent from the host-emulation fixture of tests/emul
         lib.adfwi_misfit_workspace_bytes.restype = C.c_size_t
         lib.adfwi_misfit_workspace_bytes.argtypes = [C.POINTER(MisfitDesc)]

@@ -154,6 +154,20 @@ __device__ __forceinline__ void issue_stage(const Cursor& c, unsigned char* smem
     tma_load_3d(st + 2 * RECT_BYTES / 4, t2, c.X0 - HX, c.Z0 - HZ, c.s, bar + k);
 }
 
+// TMA prefetch of a box into L2 (no shared-memory destination): the adjoint reads its history planes with plain 128-bit loads,
+// which then hit L2 instead of paying a DRAM round trip on the critical path
+__device__ __forceinline__ void acf_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+struct HistMaps { const CUtensorMap *s, *dx, *dz; };
+template <bool G2> __device__ __forceinline__ void adj_prefetch_hist(const Cursor& c, const HistMaps& hm, int hist_len, int tl)
+{
+    const int pl = c.s * hist_len + tl;
+    acf_prefetch_3d(hm.s, c.X0, c.Z0, pl);
+    if (G2) { acf_prefetch_3d(hm.dx, c.X0, c.Z0, pl); acf_prefetch_3d(hm.dz, c.X0, c.Z0, pl); }
+}
+
 // programmatic dependent launch: the next time step's grid may become resident while this one drains
 // (its prologue -- barrier init, coefficient loads -- overlaps our tail); it must not touch anything we
 // produce before griddep_wait() returns, i.e. before this grid has completed and flushed.
@@ -435,7 +449,7 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 // -- needs no coefficient at all.  Cells outside a region have alpha2 = 0 there and never feed back.
 // ------------------------------------------------------------------------------------------
 template <bool FS, bool PML, bool G2>
-__device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw,
+__device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw, const HistMaps& hm,
                                          const FGeom& g, const AdjArgs& a, unsigned char* smem_raw, uint64_t* bar,
                                          uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
@@ -481,7 +495,7 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < ADJ_STAGES; ++k)
-            if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+            if (pc.valid) { if (tid == 0) { issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); adj_prefetch_hist<G2>(pc, hm, a.hist_len, a.tl); } pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
     }
     __syncthreads();
 
@@ -580,9 +594,23 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
             float4 M[7];
 #pragma unroll
             for (int q = 0; q < 7; ++q) M[q] = ld4(mps + R.so2 + (q - 1) * RX);
+            // density gradient: the two extra history planes are loaded one row ahead of their use (register double buffer)
+            const size_t hrow0 = ((size_t)s * a.hist_len + a.tl) * g.plane + (size_t)gz2 * ld + gx2;
+            float4 hu_n = make_float4(0.f, 0.f, 0.f, 0.f), hw_n = hu_n;
+            if (G2 && col2ok && gz2 < g.nzp) {
+                hu_n = __ldcs(reinterpret_cast<const float4*>(a.hist_dx + hrow0)); hw_n = __ldcs(reinterpret_cast<const float4*>(a.hist_dz + hrow0));
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int gz = gz2 + j;
+                const float4 hu = hu_n, hw = hw_n;
+                if (G2 && j < 3) {
+                    hu_n = make_float4(0.f, 0.f, 0.f, 0.f); hw_n = hu_n;
+                    if (col2ok && gz + 1 < g.nzp) {
+                        hu_n = __ldcs(reinterpret_cast<const float4*>(a.hist_dx + hrow0 + (size_t)(j + 1) * ld));
+                        hw_n = __ldcs(reinterpret_cast<const float4*>(a.hist_dz + hrow0 + (size_t)(j + 1) * ld));
+                    }
+                }
                 const float* mr = mps + R.so2 + j * RX;
                 const float mL = mr[-1];
                 const float2 mR = ld2(mr + 4);
@@ -629,12 +657,6 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
                     // density gradient (4T, 5T): g_alpha2 -= lambda_u * D+x p + lambda_w * D+z p with the post-injection, post-6T
                     // cotangents.  The staged state is mu = alpha2 * lambda (zero outside a field's region), so the sum of
                     // mu * D p is accumulated here and divided by alpha2 once, when the partial planes are reduced.
-                    float4 hu = make_float4(0.f, 0.f, 0.f, 0.f), hw = hu;
-                    if (col2ok && gz < g.nzp) {
-                        const size_t ho = ((size_t)s * a.hist_len + a.tl) * g.plane + (size_t)gz * ld + gx2;
-                        hu = __ldcs(reinterpret_cast<const float4*>(a.hist_dx + ho));
-                        hw = __ldcs(reinterpret_cast<const float4*>(a.hist_dz + ho));
-                    }
                     g2acc[j].x = g2acc[j].x - (luo.x * hu.x + lwo.x * hw.x); g2acc[j].y = g2acc[j].y - (luo.y * hu.y + lwo.y * hw.y);
                     g2acc[j].z = g2acc[j].z - (luo.z * hu.z + lwo.z * hw.z); g2acc[j].w = g2acc[j].w - (luo.w * hu.w + lwo.w * hw.w);
                 }
@@ -642,7 +664,7 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
         }
         if (inject || (FS && tzi == 0)) fence_proxy_async();   // generic-proxy writes to the stage precede its TMA refill
         __syncthreads();
-        if (pc.valid) { if (tid == 0) issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
+        if (pc.valid) { if (tid == 0) { issue_stage(pc, smem_raw, bar, k, tm_lp, tm_lu, tm_lw); adj_prefetch_hist<G2>(pc, hm, a.hist_len, a.tl); } pc.next(g, a.s_begin, a.s_end, a.chunk, a.nchunks); }
         stage = (stage + 1 == ADJ_STAGES) ? 0 : stage + 1;
     }
 #pragma unroll
@@ -658,8 +680,10 @@ __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtenso
 template <bool FS, bool G2>
 __global__ void __launch_bounds__(NTHREADS, 2)
 ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ CUtensorMap tm_lu,
-             const __grid_constant__ CUtensorMap tm_lw, const FGeom g, const AdjArgs a)
+             const __grid_constant__ CUtensorMap tm_lw, const __grid_constant__ CUtensorMap tm_hs,
+             const __grid_constant__ CUtensorMap tm_hx, const __grid_constant__ CUtensorMap tm_hz, const FGeom g, const AdjArgs a)
 {
+    HistMaps hm; hm.s = &tm_hs; hm.dx = &tm_hx; hm.dz = &tm_hz;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = (uint64_t*)(smem_raw + ADJ_STAGES * STAGE_BYTES + 2 * RECT_BYTES + TSM_BYTES);
     int* s_sz = (int*)(bar + 4);
@@ -679,8 +703,8 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
         const bool first = item == (int)blockIdx.x;
-        if (a.tflags[tile]) adj_tile<FS, true, G2>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
-        else                adj_tile<FS, false, G2>(&tm_lp, &tm_lu, &tm_lw, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
+        if (a.tflags[tile]) adj_tile<FS, true, G2>(&tm_lp, &tm_lu, &tm_lw, hm, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
+        else                adj_tile<FS, false, G2>(&tm_lp, &tm_lu, &tm_lw, hm, g, a, smem_raw, bar, par, stage, pc, s_sz, s_sx, R, tid, tile, s_lo, s_hi, chunk, first);
         __syncthreads();
     }
 }
@@ -967,7 +991,7 @@ int acf_setup(const FPlan& P, cudaStream_t st, const float* const* coef, const i
     return ADFWI_OK;
 }
 
-struct StepMaps { CUtensorMap st[2][3]; CUtensorMap lam[2][3]; };
+struct StepMaps { CUtensorMap st[2][3]; CUtensorMap lam[2][3]; CUtensorMap hist[3]; };
 
 // launch with the programmatic-stream-serialization attribute (PDL): see griddep_wait() in the kernels
 template <typename Kern, typename... Args>
@@ -997,6 +1021,13 @@ int acf_make_maps(const FPlan& P, StepMaps* M)
             if (rc) return rc;
             if (P.save) { rc = make_tmap_f32(&M->lam[b][f], P.lam[b][f], 3, g.nxp, g.ld, g.nzp, P.ns, RX, RZ); if (rc) return rc; }
         }
+    if (P.save) {        // history planes [ns*K][nzp][ld] for the L2 prefetch of the adjoint (boxes of one tile, no halo)
+        const float* h[3] = {P.hist, P.need_g2 ? P.hist_dx : P.hist, P.need_g2 ? P.hist_dz : P.hist};
+        for (int f = 0; f < 3; ++f) {
+            const int rc = make_tmap_f32(&M->hist[f], h[f], 3, g.ld, g.ld, g.nzp, (uint64_t)P.ns * P.K, TX, TZ);
+            if (rc) return rc;
+        }
+    }
     return 0;
 }
 
@@ -1334,7 +1365,7 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
                 const int grid = acf_grid(P, se - sb, &a.nchunks);
                 {
                     TimedLaunch tl_(KC_AC_ADJ_FUSED, st);
-#define LA(FSv, G2v) ADFWI_CUDA(acf_launch(ac_adj_fused<FSv, G2v>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], g, a))
+#define LA(FSv, G2v) ADFWI_CUDA(acf_launch(ac_adj_fused<FSv, G2v>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], M.hist[0], M.hist[1], M.hist[2], g, a))
                     if (P.FS) { if (P.need_g2) LA(true, true); else LA(true, false); }
                     else      { if (P.need_g2) LA(false, true); else LA(false, false); }
 #undef LA

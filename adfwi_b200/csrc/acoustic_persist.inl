@@ -196,7 +196,9 @@ acp_fwd(const PGeom g, const PFwdArgs a)
                 const float4 um = ld4(ur);
                 const float uR = ur[4];
                 const float4 w0 = ld4(w + o), wm1 = ld4(w + o - pitch), wp1 = ld4(w + o + pitch), wm2 = ld4(w + o - 2 * pitch);
-                const float4 po = ld4(p + o), A1 = ld4(S.a1 + oc), T1 = ld4(S.t1 + oc);
+                // row fs-1 of the first strip is written by the owner of row fs+1 (mirror): its own owner must not touch it
+                const bool mirrored = fs_top && W[q].l() == 0;
+                const float4 po = mirrored ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(p + o), A1 = ld4(S.a1 + oc), T1 = ld4(S.t1 + oc);
                 float4 Sv, pv;
                 Sv.x = c1 * (((um.x - ul.y) + w0.x) - wm1.x) + c2 * (((um.y - ul.x) + wp1.x) - wm2.x);
                 Sv.y = c1 * (((um.y - um.x) + w0.y) - wm1.y) + c2 * (((um.z - ul.y) + wp1.y) - wm2.y);
@@ -208,16 +210,17 @@ acp_fwd(const PGeom g, const PFwdArgs a)
                 if (q == srcq) pp_addc(pv, srcc, src_cur);
                 // the owner of row fs+1 also writes the mirrored row fs-1; the owner of row fs-1 leaves it alone
                 if (fs_top && W[q].l() == 2) st4(p + o - 2 * pitch, make_float4(-pv.x, -pv.y, -pv.z, -pv.w));
-                if (!(fs_top && W[q].l() == 0)) st4(p + o, pv);
+                if (!mirrored) st4(p + o, pv);
             }
         }
         cluster_sync_all();
         pull_halo(p, g, k, 1, 2, tid);
         __syncthreads();
         // ---- velocity updates (:139-160) + free surface (:163-164), illumination ----------------------------------------------
+        // (row fs-1 of the first strip lies outside the U and W regions; its w is written by the owner of row fs)
 #pragma unroll
         for (int q = 0; q < KMAX; ++q) {
-            if (W[q].o >= 0) {
+            if (W[q].o >= 0 && !(fs_top && W[q].l() == 0)) {
                 const int o = W[q].o, oc = o - PHALO * pitch;
                 const float* pr = p + o;
                 const float pL = pr[-1];
@@ -241,7 +244,7 @@ acp_fwd(const PGeom g, const PFwdArgs a)
                 st4(u + o, uv);
                 // w[fs-1] = w[fs]: the owner of row fs also writes row fs-1
                 if (fs_top && W[q].l() == 1) st4(w + o - pitch, wv);
-                if (!(fs_top && W[q].l() == 0)) st4(w + o, wv);
+                st4(w + o, wv);
                 if (a.illum) {
                     accp[q].x += p0.x * p0.x; accp[q].y += p0.y * p0.y; accp[q].z += p0.z * p0.z; accp[q].w += p0.w * p0.w;
                     if (it >= a.last_chunk_start) { accu[q].x += uv.x * uv.x; accu[q].y += uv.y * uv.y; accu[q].z += uv.z * uv.z; accu[q].w += uv.w * uv.w; }
@@ -274,6 +277,7 @@ acp_fwd(const PGeom g, const PFwdArgs a)
         pull_halo(w, g, k, 2, 1, tid);
         __syncthreads();
     }
+    cluster_sync_all();          // no CTA may exit (and give up its shared memory) while a neighbour is still pulling rows from it
     if (a.illum) {
 #pragma unroll
         for (int q = 0; q < KMAX; ++q) {
@@ -406,10 +410,13 @@ acp_adj(const PGeom g, const PAdjArgs a)
                     const float4 v0 = pp_adj_phase1(lw, lu, lp, oh - 2 * pitch, oc - 2 * pitch, pitch, c1, c2);
                     v.x -= v0.x; v.y -= v0.y; v.z -= v0.z; v.w -= v0.w;
                 }
-                if (fs_top && W[q].l() == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                // row fs-1: lambda_p1 = 0 after 3T.  Its owner must NOT store that yet -- the owner of row fs+1 is reading the old value
+                // in this very phase; phase 2 (after the barriers) treats it as zero and writes the zero back.
+                const bool zeroed = fs_top && W[q].l() == 0;
+                if (zeroed) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 A1 = ld4(S.a1 + oc);
                 st4(ms + oh, make_float4((-A1.x) * v.x, (-A1.y) * v.y, (-A1.z) * v.z, (-A1.w) * v.w));
-                st4(lp + oc, v);                     // lambda_p1, read again by phase 2 (own cell)
+                if (!zeroed) st4(lp + oc, v);        // lambda_p1, read again by phase 2 (own cell)
             }
         }
         cluster_sync_all();
@@ -427,7 +434,7 @@ acp_adj(const PGeom g, const PAdjArgs a)
                 const float mL = mr[-1];
                 const float2 mR = ld2(mr + 4);
                 const float4 m0 = ld4(mr), mm1 = ld4(mr - pitch), mp1 = ld4(mr + pitch), mp2 = ld4(mr + 2 * pitch);
-                const float4 qp = ld4(lp + oc), luo = ld4(lu + oc), lwo = ld4(lw + oh);
+                const float4 qp = (fs_top && W[q].l() == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(lp + oc), luo = ld4(lu + oc), lwo = ld4(lw + oh);
                 const float4 t1 = ld4(S.t1 + oc), t2 = ld4(S.t2 + oc), t3 = ld4(S.t3 + oc);
                 float4 eu, ew;
                 pp_split_a2(g, gz, gx, ld4(S.a2 + oc), eu, ew);
@@ -458,6 +465,7 @@ acp_adj(const PGeom g, const PAdjArgs a)
         }
         __syncthreads();
     }
+    cluster_sync_all();          // no CTA may exit (and give up its shared memory) while a neighbour is still pulling rows from it
 #pragma unroll
     for (int q = 0; q < KMAX; ++q)
         if (W[q].o >= 0) red4(a.g1part + W[q].hz, gacc[q]);

@@ -36,6 +36,8 @@ config = {
     # False: never take the cluster-persistent small-grid kernels (whole time loop in one launch, state resident in shared
     # memory); they are used automatically when the active region fits and the history is store-all
     "persistent": os.environ.get("ADFWI_B200_PERSIST", "1") != "0",
+    # elastic shim: pad the six coefficient planes with the fused kernel (False: the eager F.pad chain, kept for cross-checks)
+    "fused_pad": os.environ.get("ADFWI_B200_FUSED_PAD", "1") != "0",
 }
 
 

@@ -170,6 +170,45 @@ def full_plane(data: torch.Tensor, nzp: int, nxp: int, pml: int, fs_offset: int,
     return p
 
 
+class _PadPlanes(torch.autograd.Function):
+    """The six replicate paddings of forward_kernel (elastic_kernels.py:935-946) + zero extension to the full grid in one kernel, and
+    their transpose in the backward pass (``adfwi_elastic_pad_*``).  Takes the planes in the reference's ragged shapes."""
+
+    @staticmethod
+    def forward(ctx, C11, C13, C33, C55, bx, bz, nz, nx, nzp, nxp, pml, top):
+        lib = _lib.load()
+        ins = [t.detach().contiguous().float() for t in (C11, C13, C33, C55, bx, bz)]
+        d = _lib.PadDesc(); d.nz, d.nx, d.nzp, d.nxp, d.pml, d.top = int(nz), int(nx), int(nzp), int(nxp), int(pml), int(top)
+        dev = ins[0].device
+        with torch.cuda.device(dev):
+            outs = [torch.empty((nzp, nxp), dtype=torch.float32, device=dev) for _ in range(6)]
+            ip, op = _lib.PtrArray6(*[t.data_ptr() for t in ins]), _lib.PtrArray6(*[t.data_ptr() for t in outs])
+            rc = lib.adfwi_elastic_pad_forward(C.byref(d), C.byref(ip), C.byref(op), torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib, rc, "adfwi_elastic_pad_forward")
+        ctx.d, ctx.shapes = d, [tuple(t.shape) for t in ins]
+        ctx.need = [ctx.needs_input_grad[i] for i in range(6)]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        lib = _lib.load()
+        dev = next(g.device for g in gs if g is not None)
+        with torch.cuda.device(dev):
+            gfull = [None if g is None else g.contiguous().float() for g in gs]
+            outs = [torch.zeros(s, dtype=torch.float32, device=dev) if (n and gfull[k] is None) else
+                    (torch.empty(s, dtype=torch.float32, device=dev) if n else None) for k, (s, n) in enumerate(zip(ctx.shapes, ctx.need))]
+            gp = _lib.PtrArray6(*[None if (g is None or o is None) else g.data_ptr() for g, o in zip(gfull, outs)])
+            op = _lib.PtrArray6(*[None if (o is None or g is None) else o.data_ptr() for g, o in zip(gfull, outs)])
+            rc = lib.adfwi_elastic_pad_backward(C.byref(ctx.d), C.byref(gp), C.byref(op), torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib, rc, "adfwi_elastic_pad_backward")
+        return (*outs, None, None, None, None, None, None)
+
+
+def _ragged_ok(planes, nz, nx):
+    want = [(nz, nx), (nz, nx), (nz, nx), (nz - 2, nx - 2), (nz, nx - 1), (nz - 1, nx)]
+    return all(torch.is_tensor(t) and t.is_cuda and tuple(t.shape) == w for t, w in zip(planes, want))
+
+
 def forward_kernel(nx: int, nz: int, dx: float, dz: float, nt: int, dt: float,
                    nabc: int, free_surface: bool,
                    src_x: torch.Tensor, src_z: torch.Tensor, src_n: int, src_v: torch.Tensor, MT: torch.Tensor,
@@ -202,7 +241,11 @@ def forward_kernel(nx: int, nz: int, dx: float, dz: float, nt: int, dt: float,
     dev = C11.device
     nxp = nx + 2 * nabc
     nzp = nz + (nabc + NN if free_surface else 2 * nabc + NN)
-    planes = [full_plane(t, nzp, nxp, nabc, NN, free_surface) for t in (C11, C13, C33, C55, bx, bz)]
+    if config.get("fused_pad", True) and _ragged_ok((C11, C13, C33, C55, bx, bz), nz, nx):
+        # the reference's own plane shapes (ADFWI/model/parameters.py:199-212): one fused pad kernel (and one transpose per plane)
+        planes = list(_PadPlanes.apply(C11, C13, C33, C55, bx, bz, nz, nx, nzp, nxp, nabc, NN if free_surface else NN + nabc))
+    else:
+        planes = [full_plane(t, nzp, nxp, nabc, NN, free_surface) for t in (C11, C13, C33, C55, bx, bz)]
     if pml:
         if bcx is None or bcz is None:
             raise ValueError("adfwi_b200: abc_type 'PML' needs bcx and bcz (note: the reference propagator only builds "

@@ -234,6 +234,31 @@ int adfwi_regularization_forward(const adfwi_regularization_desc* desc, const fl
 int adfwi_regularization_backward(const adfwi_regularization_desc* desc, const float* m, const float* grad_value, float* g_m,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Model-side producers of the elastic coefficient planes.
+ *
+ * adfwi_elastic_moduli_*: replaces thomsen_to_elastic_moduli (ADFWI/model/parameters.py:71-107), the TI fill-in
+ * C55 = C44 / HTI swap (:156-181), b = 1/rho (:47-69) and parameter_staggered_grid (:184-213) -- and their autograd
+ * mirror.  vp, vs, rho, eps, delta: [nz][nx].  planes: C11, C13, C33 [nz][nx]; C55 [nz-2][nx-2]; bx [nz][nx-1];
+ * bz [nz-1][nx] (the ragged shapes the reference hands to forward_kernel).  backward: g_planes in the same shapes,
+ * outputs [nz][nx], each nullable.  gamma does not reach the P-SV planes (C66 is unused there).
+ *
+ * adfwi_elastic_pad_*: replaces the six pad_torchSingle calls of forward_kernel
+ * (ADFWI/propagator/elastic_kernels.py:176-216, :935-946) plus the zero extension to the full grid that the region
+ * slices of :303-310 imply: planes in their own shapes -> six full [nzp][nxp] planes; backward = transpose.
+ * pml = nabc, top = fs_offset (free surface) or fs_offset + nabc.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int32_t nz, nx; int32_t hti; int32_t reserved; } adfwi_elastic_moduli_desc;
+typedef struct { int32_t nz, nx, nzp, nxp, pml, top; int32_t reserved[2]; } adfwi_elastic_pad_desc;
+
+int adfwi_elastic_moduli_forward(const adfwi_elastic_moduli_desc* desc, const float* vp, const float* vs, const float* rho,
+                                 const float* eps, const float* delta, float* const* planes, void* stream);
+int adfwi_elastic_moduli_backward(const adfwi_elastic_moduli_desc* desc, const float* vp, const float* vs, const float* rho,
+                                  const float* eps, const float* delta, const float* const* g_planes,
+                                  float* g_vp, float* g_vs, float* g_rho, float* g_eps, float* g_delta, void* stream);
+int adfwi_elastic_pad_forward(const adfwi_elastic_pad_desc* desc, const float* const* planes, float* const* full, void* stream);
+int adfwi_elastic_pad_backward(const adfwi_elastic_pad_desc* desc, const float* const* g_full, float* const* g_planes, void* stream);
+
 /* misc */
 const char* adfwi_strerror(int code);
 int adfwi_abi_version(void);

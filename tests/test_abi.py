@@ -44,7 +44,8 @@ def test_struct_layout_matches_header(tmp_path):
     assert ctypes.sizeof(_lib.AcousticDesc) == 4 * 19
     assert ctypes.sizeof(_lib.ElasticDesc) == 4 * 28
     mirrors = {"adfwi_acoustic_desc": _lib.AcousticDesc, "adfwi_elastic_desc": _lib.ElasticDesc, "adfwi_gradproc_desc": _lib.GradProcDesc,
-               "adfwi_misfit_desc": _lib.MisfitDesc, "adfwi_regularization_desc": _lib.RegularizationDesc}
+               "adfwi_misfit_desc": _lib.MisfitDesc, "adfwi_regularization_desc": _lib.RegularizationDesc,
+               "adfwi_elastic_moduli_desc": _lib.ModuliDesc, "adfwi_elastic_pad_desc": _lib.PadDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "adfwi_b200.h"', 'int main(void) {']
     for cname, cls in mirrors.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
