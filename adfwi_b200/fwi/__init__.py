@@ -17,6 +17,8 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 import torch
 
+from ..propagator.acoustic_kernels import pick_shots
+
 
 def l2_waveform_misfit(obs: torch.Tensor, syn: torch.Tensor, dt: float = 1.0) -> torch.Tensor:
     """sum over traces of sqrt(sum_t (obs-syn)^2 dt)   (fwi/misfit/L2.py:25-28)."""
@@ -49,7 +51,7 @@ def acoustic_gradient(propagator, obs_p: torch.Tensor, shots: Optional[Sequence[
     illum = None
     for pos in shot_batches(len(shots), batch_size):
         rec = propagator.forward(shot_index=shots[pos], checkpoint_segments=checkpoint_segments)
-        obs = obs_loader(pos) if obs_loader is not None else obs_p[pos]
+        obs = obs_loader(pos) if obs_loader is not None else pick_shots(obs_p, pos)
         loss = misfit(rec["p"], obs)
         loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
@@ -70,7 +72,7 @@ def elastic_gradient(propagator, obs: dict, shots: Optional[Sequence[int]] = Non
     illum = None
     for pos in shot_batches(len(shots), batch_size):
         rec = propagator.forward(shot_index=shots[pos], fd_order=fd_order, checkpoint_segments=checkpoint_segments)
-        ob = obs_loader(pos) if obs_loader is not None else {c: obs[c][pos] for c in components}
+        ob = obs_loader(pos) if obs_loader is not None else {c: pick_shots(obs[c], pos) for c in components}
         loss = sum(l2_waveform_misfit(ob[c], rec[c], propagator.dt) for c in components)
         loss.backward()
         total = loss.detach() if total is None else total + loss.detach()

@@ -168,6 +168,33 @@ def pad_replicate(v: torch.Tensor, pml: int) -> torch.Tensor:
     return F.pad(v.float()[None, None], (pml, pml, pml, pml), mode="replicate")[0, 0]
 
 
+_SCALARS = {}
+
+
+def _device_scalar(value, device):
+    """0-dim fp32 device tensor, created once per (value, device): building it per call is a blocking host-to-device copy, i.e. a
+    stream synchronisation on every forward."""
+    key = (value, str(device))
+    t = _SCALARS.get(key)
+    if t is None:
+        t = _SCALARS[key] = torch.tensor(value, dtype=torch.float32, device=device)
+    return t
+
+
+def pick_shots(t, shot_index):
+    """``t[shot_index]`` as the reference propagators write it (acoustic_propagator.py:142-145); a contiguous ascending index -- what the
+    reference's shot batches are (acoustic_fwi.py:136-138) -- becomes a slice: no index tensor, no host-to-device copy, no sync."""
+    if shot_index is None:
+        return t
+    if isinstance(shot_index, slice):
+        return t[shot_index]
+    import numpy as np
+    idx = np.asarray(shot_index.cpu() if torch.is_tensor(shot_index) else shot_index)
+    if idx.ndim == 1 and idx.size and idx.dtype.kind in "iu" and idx[0] >= 0 and np.array_equal(idx, np.arange(idx[0], idx[0] + idx.size)):
+        return t[int(idx[0]):int(idx[0]) + idx.size]
+    return t[shot_index]
+
+
 def coefficient_planes(v, rho, damp, dt, dz, nabc, free_surface):
     """alpha1, alpha2, kappa1, kappa2, kappa3 with the reference's rounding order (:257-265)."""
     c = pad_replicate(v, nabc)
@@ -176,7 +203,7 @@ def coefficient_planes(v, rho, damp, dt, dz, nabc, free_surface):
     fs = nabc if free_surface else 1
     # `tensor / python_float` on CUDA multiplies by the rounded reciprocal; the CPU reference (the
     # parity oracle) performs a true division, so divide by a 0-dim device tensor instead.
-    dz_t = torch.tensor(float(dz), dtype=torch.float32, device=c.device)
+    dz_t = _device_scalar(float(dz), c.device)
     alpha1 = den * c * c * dt / dz_t
     kappa1 = damp * dt
     alpha2 = dt / (den * dz)

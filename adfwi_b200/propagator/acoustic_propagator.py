@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
-from .acoustic_kernels import forward_kernel
+from .acoustic_kernels import forward_kernel, pick_shots
 from .boundary_condition import bc_gerjan, bc_pml, bc_sincos
 
 _MODEL_ATTRS = ("ox", "oz", "dx", "dz", "nx", "nz", "abc_type", "nabc", "free_surface", "vp", "rho", "forward")
@@ -81,7 +81,7 @@ class AcousticPropagator(torch.nn.Module):
         """Forward simulation of the selected shots; returns the record dict of ``forward_kernel``."""
         model = self.model if model is None else model
         model.forward()
-        pick = (lambda t: t) if shot_index is None else (lambda t: t[shot_index])
+        pick = lambda t: pick_shots(t, shot_index)
         src_x, src_z, wavelet = pick(self.src_x), pick(self.src_z), pick(self.wavelet)
         return forward_kernel(
             self.nx, self.nz, self.dx, self.dz, self.nt, self.dt,

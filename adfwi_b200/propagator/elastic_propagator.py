@@ -6,6 +6,7 @@ from typing import Optional
 
 import torch
 
+from .acoustic_kernels import pick_shots
 from .acoustic_propagator import _to_tensor
 from .boundary_condition import bc_gerjan, bc_pml_xz, bc_sincos
 from .elastic_kernels import forward_kernel
@@ -65,7 +66,7 @@ class ElasticPropagator(torch.nn.Module):
     def forward(self, model=None, shot_index=None, fd_order=4, checkpoint_segments=1):
         model = self.model if model is None else model
         model.forward()
-        pick = (lambda t: t) if shot_index is None else (lambda t: t[shot_index])
+        pick = lambda t: pick_shots(t, shot_index)
         src_x, src_z = pick(self.src_x), pick(self.src_z)
         return forward_kernel(
             self.nx, self.nz, self.dx, self.dz, self.nt, self.dt,

@@ -57,12 +57,13 @@ L2_BYTES = 126e6
 
 
 def l2_note(state_bytes_per_launch, stream_bytes_per_step):
-    """config.l2: what the timed region does about the L2 (timing rule: flush it or use inputs larger than it, and say which)."""
+    """config.l2: what the timed region does about the L2 (timing rule: flush it or use inputs larger than it, and say which).
+    `state_bytes_per_launch` = the wavefield planes one launch WRITES and the next launch (next time step, same shots) reads."""
     fits = state_bytes_per_launch <= L2_BYTES
     return {"flush": "none (no explicit flush)",
             "bytes_streamed_per_step": int(stream_bytes_per_step),
             "inputs_larger_than_l2": bool(stream_bytes_per_step > 4 * L2_BYTES),
-            "state_bytes_per_launch": int(state_bytes_per_launch),
+            "state_bytes_handed_between_launches": int(state_bytes_per_launch),
             "state_fits_l2": bool(fits),
             "note": ("every timed step streams its stencil history, records and receiver cotangents through HBM (far more than the 126 MB L2), so "
                      "nothing of one step survives in L2 into the next; " +
@@ -283,26 +284,18 @@ def reference_gradient_sample(wl, ns, nt, device, reps, warmup):
 
 
 def cpu_baseline_entry(args, wl):
-    """`cpu_baseline` of the B200 arm: the unmodified reference on the host cores when its package is staged (kind "reference"),
-    else the C/OpenMP port (kind "port"); the port's warm mean is always reported beside it."""
-    from oracle import ref_loader
-    cores = os.cpu_count()
-    port_v, port_s, pns, pnt = cpu_port_warm(wl, reps=2)
-    port = {"value": port_v / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
-            "sample": f"oracle/ C port (OpenMP, all host threads), {pns} shots x {pnt} steps of the {args.workload} grid, forward+adjoint, "
-                      f"warm mean of 2, {port_s:.1f} s each"}
-    if ref_loader.available():
-        elastic = wl.get("kind") == "elastic"
-        ns, nt = (2, 20) if elastic else (2, 100)
-        try:
-            val, sec = reference_gradient_sample(wl, ns, nt, "cpu", reps=1, warmup=1)
-            return {"value": val / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "reference",
-                    "sample": f"unmodified reference (propagator.forward + Misfit_waveform_L2 + loss.backward(), checkpoint_segments=4, device='cpu', "
-                              f"torch {cores} threads), {ns} shots x {nt} steps of the {args.workload} grid, {sec:.1f} s per gradient after one warm-up",
-                    "port": port}
-        except Exception as e:
-            port["sample"] += f" (reference failed: {type(e).__name__}: {e})"
-    return port
+    """`cpu_baseline` of the B200 arm: what the reference arm measures -- the unmodified reference on the host cores when its package is
+    staged (kind "reference"), else the C/OpenMP port (kind "port"), the port always beside it -- taken in a FRESH process (this one
+    carries a CUDA context, torch's thread pools and the clock sampler, which halved the port's throughput when it ran in here)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "1", "--warmup", "1", "--no-reference-cuda"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")][-1])
+        out = dict(d["cpu_baseline"])
+        out["port"] = d.get("port")
+        return out
+    except Exception as e:
+        return {"value": None, "unit": "Gcell-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"cpu baseline run failed: {type(e).__name__}: {e}"[:300]}
 
 
 def run_reference(args, wl):
@@ -332,7 +325,7 @@ def run_reference(args, wl):
             val, sec, kind, sample = port_v, port_s, "port", port["sample"] + f" (reference failed: {type(e).__name__}: {e})"
         try:
             import torch
-            if torch.cuda.is_available():
+            if args.reference_cuda and torch.cuda.is_available():
                 cns, cnt = (2, 50) if elastic else (4, 100)
                 cv, cs = reference_gradient_sample(wl, cns, cnt, "cuda:0", reps=2, warmup=2)
                 ref_cuda = {"value": cv / 1e9, "unit": "Gcell-updates/s", "seconds_per_gradient": cs,
@@ -508,8 +501,11 @@ def run_b200(args, wl):
             if os.path.exists(tpath):
                 try:
                     tj = json.load(open(tpath))
-                    ent = tj.get(args.workload) if isinstance(tj.get(args.workload), dict) else (tj if tj.get("workload") == args.workload else None)
-                    if ent and ent.get("batch") == batch and not args.rho_grad:
+                    wkey = args.workload + ("_rho" if args.rho_grad else "")
+                    ent = tj.get(wkey) if isinstance(tj.get(wkey), dict) else (tj if (tj.get("workload") == wkey) else None)
+                    if persist:
+                        dom_key = "acp_adj" if adj >= fwd else "acp_fwd"
+                    if ent and ent.get("batch") == batch:
                         traffic = ent.get(dom_key)
                 except Exception:
                     traffic = None
@@ -544,7 +540,7 @@ def run_b200(args, wl):
             "config": {"workload": f"{args.workload}: {wl['desc']}", "shots_per_gpu": ns_local, "shots_total": ns_total,
                        "batch_size": batch, "padded_grid": [nzp, nxp], "nt": nt, "receivers": wl["nr"],
                        "gradients": ["vp", "rho"] if args.rho_grad else ["vp"],
-                       "l2": l2_note(6.0 * (G_cells or batch * nzp * nxp) * 4, (1 + (2 if args.rho_grad else 0)) * 2.0 * nzp * nxp * nt * ns_local * 4),
+                       "l2": l2_note(3.0 * (G * nzp * nxp if avg else batch * nzp * nxp) * 4, (1 + (2 if args.rho_grad else 0)) * 2.0 * nzp * nxp * nt * ns_local * 4),
                        "parallelism": f"shots sharded over {world} GPU(s), one all-reduce of the gradient"},
             "shots_per_s": ns_total * args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "ms_per_step": ms_e2e / args.steps,
@@ -555,6 +551,13 @@ def run_b200(args, wl):
             "clocks": clk,
         }
         if args.secondary and world == 1:
+            # the secondary runs are separate processes on the same GPU: hand the memory back first (a child that finds the device
+            # full of this process's cached workspace would be pushed into checkpointing and measure a recomputation sweep)
+            import gc
+            model.vp.grad = None
+            del obs, obs_host, prop, model
+            gc.collect()
+            torch.cuda.empty_cache()
             line["secondary"] = secondary_measurements(args)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -705,7 +708,7 @@ def run_b200_elastic(args, wl):
                 try:
                     # the ncu capture is taken on a shortened run (tools/profile_r01s.sh); DRAM bytes of a launch
                     # scale with the cells it advances, so the captured figure is rescaled to this run's launch size
-                    tj = json.load(open(tpath)).get(args.workload, {})
+                    tj = json.load(open(tpath)).get(args.workload + ("" if args.abc == "PML" else "_" + args.abc), {})
                     if tj.get("cells_per_launch"):
                         traffic = int(tj["el_adj" if adj >= fwd else "el_fwd"] * cells / tj["cells_per_launch"])
                 except Exception:
@@ -741,7 +744,7 @@ def run_b200_elastic(args, wl):
             "config": {"workload": f"{args.workload}: {wl['desc']}", "shots_per_gpu": ns_local, "shots_total": ns_total,
                        "batch_size": batch, "padded_grid": [nzp, nxp], "nt": nt, "receivers": wl["nr"], "gradients": list(grads), "abc_type": args.abc,
                        "fd_order": args.order,
-                       "l2": l2_note((20.0 if args.abc == "PML" else 10.0) * batch * nzp * nxp * 4, 8 * 2.0 * nzp * nxp * nt * ns_local * 4),
+                       "l2": l2_note((10.0 if args.abc == "PML" else 5.0) * batch * nzp * nxp * 4, 8 * 2.0 * nzp * nxp * nt * ns_local * 4),
                        "parallelism": f"shots sharded over {world} GPU(s), one all-reduce of the gradients"},
             "shots_per_s": ns_total * args.steps / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "ms_per_step": ms_e2e / args.steps,
@@ -758,7 +761,7 @@ def run_b200_elastic(args, wl):
 
 SECONDARY = [
     # (label, extra command-line arguments): short, bounded runs of the other BASELINE.json configurations, each with its own roofline
-    ("C1 full (40 shots, nt 1600)", ["--workload", "C1"]),
+    ("C1 full (40 shots, nt 1600)", ["--workload", "C1", "--steps", "8"]),
     ("C2 with the density gradient (vp + rho), nt 400 x 10 shots", ["--workload", "C2", "--rho-grad", "--nt", "400", "--shots", "10", "--batch", "10"]),
     ("C3 iso-elastic split-PML, nt 400 x 15 shots", ["--workload", "C3", "--nt", "400", "--shots", "15", "--batch", "15"]),
     ("C3 iso-elastic sponge (ABL), nt 400 x 15 shots", ["--workload", "C3", "--abc", "gerjan", "--nt", "400", "--shots", "15", "--batch", "15"]),
@@ -811,6 +814,8 @@ def main():
     ap.add_argument("--no-secondary", dest="secondary", action="store_false",
                     help="skip the short secondary measurements of the other configurations appended to the default (C2, 1 GPU) line")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false", help="skip the host-side cpu_baseline leg")
+    ap.add_argument("--no-reference-cuda", dest="reference_cuda", action="store_false",
+                    help="reference arm: skip timing the unmodified reference with device='cuda' beside its CPU number")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
