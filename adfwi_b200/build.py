@@ -18,7 +18,7 @@ LIB = os.path.join(CSRC, "libadfwi_b200.so")
 SOURCES = ["api.cu", "acoustic.cu", "acoustic_fused.cu", "elastic.cu", "elastic_fused.cu", "gradproc.cu", "objective.cu", "parameters.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC,-O2", "-shared",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC,-O2", "-shared", "-ldl",
 ]
 
 

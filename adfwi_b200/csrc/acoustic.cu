@@ -469,6 +469,7 @@ extern "C" int adfwi_acoustic_forward(const adfwi_acoustic_desc* desc,
                                       float* illum_p, float* illum_u, float* illum_w,
                                       void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_acoustic_forward");
     AcPlan P;
     int rc = ac_make_plan(desc, workspace, &P);
     if (rc) return rc;
@@ -542,6 +543,7 @@ extern "C" int adfwi_acoustic_backward(const adfwi_acoustic_desc* desc,
                                        float* g_alpha1, float* g_alpha2, float* g_src_v,
                                        void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_acoustic_backward");
     AcPlan P;
     int rc = ac_make_plan(desc, workspace, &P);
     if (rc) return rc;

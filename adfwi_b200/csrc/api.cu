@@ -3,6 +3,9 @@
 
 #include <mutex>
 #include <vector>
+#ifndef ADFWI_HOST_EMUL
+#include <nvtx3/nvToolsExt.h>
+#endif
 
 namespace adfwi {
 std::atomic<uint64_t> g_launches{0};
@@ -35,6 +38,9 @@ TimedLaunch::~TimedLaunch()
     std::lock_guard<std::mutex> lk(g_tm);
     cudaEventRecord(g_samples[slot].b, st);
 }
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 #endif
 }  // namespace adfwi
 

@@ -54,6 +54,15 @@ struct TimedLaunch {      // RAII: start event in the constructor, stop event in
 };
 #endif
 
+// NVTX range around every compute entry point of the C ABI (nvtx3 is header-only: a no-op function-pointer test unless a tool such
+// as ncu --nvtx / nsys injected itself); `ncu --nvtx --nvtx-include "adfwi_acoustic_backward/"` then filters by entry point.
+#ifdef ADFWI_HOST_EMUL
+struct NvtxRange { explicit NvtxRange(const char*) {} };
+#else
+struct NvtxRange { explicit NvtxRange(const char* name); ~NvtxRange(); };
+#endif
+#define ADFWI_NVTX(name) ::adfwi::NvtxRange nvtx_range__(name)
+
 #define ADFWI_LAUNCH_CHECK()                                   \
     do {                                                       \
         ::adfwi::g_launches.fetch_add(1, std::memory_order_relaxed); \

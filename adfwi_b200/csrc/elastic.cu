@@ -773,6 +773,7 @@ extern "C" int adfwi_elastic_forward(const adfwi_elastic_desc* desc, const float
                                      float* const* rcv, float* const* illum,
                                      void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_elastic_forward");
     ElPlan P;
     int rc = el_make_plan(desc, workspace, &P);
     if (rc) return rc;
@@ -798,6 +799,7 @@ extern "C" int adfwi_elastic_backward(const adfwi_elastic_desc* desc, const floa
                                       const float* const* g_rcv, float* const* g_coef, float* g_src_v,
                                       void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_elastic_backward");
     ElPlan P;
     int rc = el_make_plan(desc, workspace, &P);
     if (rc) return rc;

@@ -2199,7 +2199,8 @@ struct EFPlan {
     EGeom g;
     int ns, nr, NN, FS, save, n_segments, nz, nx, nabc, zoff;
     int K, nseg, nckpt, G;
-    int chunk, nchunks;
+    int chunk, nchunks;          // shots per (tile, chunk) item of the forward kernels
+    int chunk_b, nchunks_b;      // ... of the reverse kernels (longer walks: the per-item gradient read-modify-write is amortised over them)
     int cprows; size_t cpplane;
     float* pack; unsigned char* tflags;
     float* planes; int nfields;
@@ -2208,6 +2209,34 @@ struct EFPlan {
     int *rcv_cnt, *rcv_start, *rcv_cursor, *rcv_id, *rcv_zx; unsigned char* rcv_nbr;
     size_t bytes;
 };
+
+// Shots per (tile, chunk) item.  A launch of G shots is cut into ntiles * ceil(G / chunk) items which the resident CTAs draw
+// dynamically.  Cost model (shot-steps of one CTA; fitted to sweeps on the C3 and C4 grids, profiles/r02w_el_items.md):
+//     T(chunk) = ntiles * (G + c0 * nchunks) / ncta  +  (chunk + c0)
+// -- the work with a fixed cost c0 per item (coefficient tables, pipeline fill; the reverse kernels add the read-modify-write of
+// six gradient partial planes: c0 = 1.5 against 0.5 for the forward kernels), plus a tail of about one item.  Ragged splits
+// (15 = 4+4+4+3) pay c0 for the short item too, which is why exact divisors tend to win.
+inline int elf_pick_chunk(int G, int ntiles, int ncta, float c0)
+{
+    int best = 1; float tbest = 3.0e38f;
+    const int cmax = G < CMAX ? G : CMAX;
+    for (int c = 1; c <= cmax; ++c) {
+        const float t = (float)ntiles * ((float)G + c0 * (float)cdiv(G, c)) / (float)ncta + ((float)c + c0);
+        if (t < tbest) { tbest = t; best = c; }
+    }
+    return best;
+}
+// desc->reserved[1] (both directions) and reserved[2] (reverse kernels only) override the model (tuning sweeps, tests)
+inline void elf_plan_chunks(const adfwi_elastic_desc* d, int G, int ntiles, int nsm, int* chunk, int* nchunks, int* chunk_b, int* nchunks_b)
+{
+    const int ncta = CTAS_PER_SM * nsm;
+    int cf = d->reserved[1] > 0 ? d->reserved[1] : elf_pick_chunk(G, ntiles, ncta, 0.5f);
+    int cb = d->reserved[2] > 0 ? d->reserved[2] : d->reserved[1] > 0 ? d->reserved[1] : elf_pick_chunk(G, ntiles, ncta, 1.5f);
+    cf = cf < 1 ? 1 : (cf > CMAX ? CMAX : cf); if (cf > G) cf = G;
+    cb = cb < 1 ? 1 : (cb > CMAX ? CMAX : cb); if (cb > G) cb = G;
+    *chunk = cf; *nchunks = cdiv(G, cf);
+    *chunk_b = cb; *nchunks_b = cdiv(G, cb);
+}
 
 int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
 {
@@ -2233,12 +2262,7 @@ int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
     if (G <= 0 || G > d->ns) G = d->ns;
     P->G = G;
     const int ntiles = g.ntx * g.ntz;
-    int nchunks = d->reserved[1] > 0 ? cdiv(G, d->reserved[1]) : (6 * CTAS_PER_SM * nsm + ntiles - 1) / ntiles;    // >= ~6 rounds over the resident CTAs
-    if (nchunks < 1) nchunks = 1;
-    if (nchunks > G) nchunks = G;
-    int chunk = cdiv(G, nchunks);
-    if (chunk > CMAX) chunk = CMAX;
-    P->chunk = chunk; P->nchunks = cdiv(G, chunk);
+    elf_plan_chunks(d, G, ntiles, nsm, &P->chunk, &P->nchunks, &P->chunk_b, &P->nchunks_b);
     Carver cv(ws);
     const size_t sp = (size_t)d->ns * g.plane;
     P->pack = cv.take<float>(8 * P->cpplane);
@@ -2253,7 +2277,7 @@ int elf_make_plan(const adfwi_elastic_desc* d, void* ws, EFPlan* P, int nsm)
     P->counters = cv.take<int>(P->ncounters);
     P->hist = P->ckpt = P->gpart = nullptr;
     if (P->save) {
-        P->gpart = cv.take<float>((size_t)P->nchunks * 6 * g.plane);
+        P->gpart = cv.take<float>((size_t)P->nchunks_b * 6 * g.plane);
         if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * 10 * sp);
         P->hist = cv.take<float>((size_t)K * NHIST * sp);
     }
@@ -2368,9 +2392,10 @@ template <int NN> int elf_init_kernels()
     return rc;
 }
 
-inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid)
+inline Walk elf_walk(const EFPlan& P, int sb, int se, int* grid, bool reverse = false)
 {
-    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = P.chunk; w.nchunks = cdiv(se - sb, P.chunk); w.counter = nullptr;
+    const int chunk = reverse ? P.chunk_b : P.chunk;
+    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = chunk; w.nchunks = cdiv(se - sb, chunk); w.counter = nullptr;
     const int nitems = P.g.ntx * P.g.ntz * w.nchunks;
     const int cap = CTAS_PER_SM * elf_num_sms();
     *grid = nitems < cap ? nitems : cap;
@@ -2516,7 +2541,7 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
     const EGeom& g = P.g;
     const int nt = g.nt;
     const bool pdl = elf_use_pdl();
-    ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks * 6 * g.plane, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks_b * 6 * g.plane, st));
     ADFWI_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(int) * P.ncounters, st));
     int seq = 0;
     for (int sb = 0; sb < P.ns; sb += P.G) {
@@ -2524,7 +2549,7 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
         int rc = elf_zero_fields(P, st, P_LV, P_COUNT, sb, se);
         if (rc) return rc;
         int grid;
-        const Walk w = elf_walk(P, sb, se, &grid);
+        const Walk w = elf_walk(P, sb, se, &grid, true);
         int lcur = 0;
         for (int seg = P.nseg - 1; seg >= 0; --seg) {
             const int t0 = seg * P.K, t1 = t0 + P.K < nt ? t0 + P.K : nt;
@@ -2582,7 +2607,7 @@ int elf_backward_t(const EFPlan& P, const EMaps& M, cudaStream_t st, const EArgs
         }
     }
     for (int k = 0; k < 6; ++k) {
-        elf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.plane, P.nchunks, k, P.gpart, g_coef[k]);
+        elf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.plane, P.nchunks_b, k, P.gpart, g_coef[k]);
         ADFWI_LAUNCH_CHECK();
     }
     return ADFWI_OK;
@@ -2596,7 +2621,7 @@ struct EAPlan {
     EGeom g;
     int ns, nr, NN, FS, save, n_segments, nz, nx, nabc, zoff;
     int K, nseg, nckpt, G;
-    int chunk, nchunks;
+    int chunk, nchunks, chunk_b, nchunks_b;      // as in EFPlan
     int cprows; size_t cpplane;
     float* pack;
     float* planes; int nfields;
@@ -2632,12 +2657,7 @@ int ela_make_plan(const adfwi_elastic_desc* d, void* ws, EAPlan* P, int nsm)
     if (G <= 0 || G > d->ns) G = d->ns;
     P->G = G;
     const int ntiles = g.ntx * g.ntz;
-    int nchunks = d->reserved[1] > 0 ? cdiv(G, d->reserved[1]) : (6 * CTAS_PER_SM * nsm + ntiles - 1) / ntiles;
-    if (nchunks < 1) nchunks = 1;
-    if (nchunks > G) nchunks = G;
-    int chunk = cdiv(G, nchunks);
-    if (chunk > CMAX) chunk = CMAX;
-    P->chunk = chunk; P->nchunks = cdiv(G, chunk);
+    elf_plan_chunks(d, G, ntiles, nsm, &P->chunk, &P->nchunks, &P->chunk_b, &P->nchunks_b);
     Carver cv(ws);
     const size_t sp = (size_t)d->ns * g.plane;
     P->pack = cv.take<float>(8 * P->cpplane);
@@ -2653,7 +2673,7 @@ int ela_make_plan(const adfwi_elastic_desc* d, void* ws, EAPlan* P, int nsm)
     P->hist = P->ckpt = P->gpart = nullptr;
     P->ckpt_stride = 5 * sp + (size_t)2 * d->ns * g.ld;
     if (P->save) {
-        P->gpart = cv.take<float>((size_t)P->nchunks * 6 * g.plane);
+        P->gpart = cv.take<float>((size_t)P->nchunks_b * 6 * g.plane);
         if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * P->ckpt_stride);
         P->hist = cv.take<float>((size_t)K * ANHIST * sp);
     }
@@ -2728,9 +2748,10 @@ template <int NN> int ela_init_kernels()
     return rc;
 }
 
-inline Walk ela_walk(const EAPlan& P, int sb, int se, int* grid)
+inline Walk ela_walk(const EAPlan& P, int sb, int se, int* grid, bool reverse = false)
 {
-    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = P.chunk; w.nchunks = cdiv(se - sb, P.chunk); w.counter = nullptr;
+    const int chunk = reverse ? P.chunk_b : P.chunk;
+    Walk w; w.s_begin = sb; w.s_end = se; w.chunk = chunk; w.nchunks = cdiv(se - sb, chunk); w.counter = nullptr;
     const int nitems = P.g.ntx * P.g.ntz * w.nchunks;
     const int cap = CTAS_PER_SM * elf_num_sms();
     *grid = nitems < cap ? nitems : cap;
@@ -2860,7 +2881,7 @@ int ela_backward_t(const EAPlan& P, const EAMaps& M, cudaStream_t st, const EArg
     const EGeom& g = P.g;
     const int nt = g.nt;
     const bool pdl = elf_use_pdl();
-    ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks * 6 * g.plane, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.gpart, 0, sizeof(float) * (size_t)P.nchunks_b * 6 * g.plane, st));
     ADFWI_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(int) * P.ncounters, st));
     int seq = 0;
     for (int sb = 0; sb < P.ns; sb += P.G) {
@@ -2884,7 +2905,7 @@ int ela_backward_t(const EAPlan& P, const EAMaps& M, cudaStream_t st, const EArg
                 if (seq + 1 > P.ncounters) return ADFWI_E_DIMS;
                 int grid;
                 ABArgs a;
-                a.w = ela_walk(P, sb, se, &grid);
+                a.w = ela_walk(P, sb, se, &grid, true);
                 a.w.counter = P.counters + seq++;
                 a.cp = ela_pack_ptrs(P); a.planes = P.planes; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it; a.lcur = lcur;
                 a.nr = P.nr; a.rb = ela_bucket_ptrs(P);
@@ -2901,7 +2922,7 @@ int ela_backward_t(const EAPlan& P, const EAMaps& M, cudaStream_t st, const EArg
         }
     }
     for (int k = 0; k < 6; ++k) {
-        elf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.plane, P.nchunks, k, P.gpart, g_coef[k]);
+        elf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.plane, P.nchunks_b, k, P.gpart, g_coef[k]);
         ADFWI_LAUNCH_CHECK();
     }
     return ADFWI_OK;

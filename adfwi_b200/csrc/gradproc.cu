@@ -210,6 +210,7 @@ extern "C" size_t adfwi_gradproc_workspace_bytes(const adfwi_gradproc_desc* d)
 
 extern "C" int adfwi_gradproc_smooth2d(int nz, int nx, int span, const double* in, double* out, void* ws, size_t ws_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_gradproc_smooth2d");
     if (!in || !out || !ws) return ADFWI_E_NULL;
     if (nz <= 0 || nx <= 0) return ADFWI_E_DIMS;
     const GPlan P = gp_plan(nz, nx, ws);
@@ -220,6 +221,7 @@ extern "C" int adfwi_gradproc_smooth2d(int nz, int nx, int span, const double* i
 extern "C" int adfwi_gradproc_forward(const adfwi_gradproc_desc* d, const float* grad, const float* forw, const double* mask,
                                       double* out, int* out_is_f32_host, void* ws, size_t ws_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_gradproc_forward");
     if (!d || !grad || !out || !ws) return ADFWI_E_NULL;
     if (d->nz <= 0 || d->nx <= 0 || d->grad_mute < 0 || d->grad_smooth < 0 || d->grad_mute > d->nz) return ADFWI_E_DIMS;
     if (d->use_illumination && !forw) return ADFWI_E_NULL;

@@ -265,6 +265,7 @@ extern "C" size_t adfwi_misfit_workspace_bytes(const adfwi_misfit_desc* desc)
 extern "C" int adfwi_misfit_forward(const adfwi_misfit_desc* desc, const float* syn, const float* obs, float* loss,
                                     void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_misfit_forward");
     MfPlan P;
     int rc = mf_make_plan(desc, workspace, &P);
     if (rc) return rc;
@@ -285,6 +286,7 @@ extern "C" int adfwi_misfit_forward(const adfwi_misfit_desc* desc, const float* 
 extern "C" int adfwi_misfit_adjoint_source(const adfwi_misfit_desc* desc, const float* syn, const float* obs, const float* grad_loss,
                                            float* g_syn, void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_misfit_adjoint_source");
     MfPlan P;
     int rc = mf_make_plan(desc, workspace, &P);
     if (rc) return rc;
@@ -315,6 +317,7 @@ extern "C" size_t adfwi_regularization_workspace_bytes(const adfwi_regularizatio
 extern "C" int adfwi_regularization_forward(const adfwi_regularization_desc* desc, const float* m, float* value,
                                             void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_regularization_forward");
     RgGeom g;
     int rc = rg_geom(desc, &g);
     if (rc) return rc;
@@ -333,6 +336,7 @@ extern "C" int adfwi_regularization_forward(const adfwi_regularization_desc* des
 extern "C" int adfwi_regularization_backward(const adfwi_regularization_desc* desc, const float* m, const float* grad_value, float* g_m,
                                              void* workspace, size_t workspace_bytes, void* stream)
 {
+    ADFWI_NVTX("adfwi_regularization_backward");
     RgGeom g;
     int rc = rg_geom(desc, &g);
     if (rc) return rc;

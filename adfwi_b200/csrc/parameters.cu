@@ -146,6 +146,7 @@ using namespace adfwi;
 extern "C" int adfwi_elastic_moduli_forward(const adfwi_elastic_moduli_desc* desc, const float* vp, const float* vs, const float* rho,
                                             const float* eps, const float* delta, float* const* planes, void* stream)
 {
+    ADFWI_NVTX("adfwi_elastic_moduli_forward");
     MdGeom g;
     int rc = md_geom(desc, &g);
     if (rc) return rc;
@@ -162,6 +163,7 @@ extern "C" int adfwi_elastic_moduli_backward(const adfwi_elastic_moduli_desc* de
                                              const float* eps, const float* delta, const float* const* g_planes,
                                              float* g_vp, float* g_vs, float* g_rho, float* g_eps, float* g_delta, void* stream)
 {
+    ADFWI_NVTX("adfwi_elastic_moduli_backward");
     MdGeom g;
     int rc = md_geom(desc, &g);
     if (rc) return rc;
@@ -177,6 +179,7 @@ extern "C" int adfwi_elastic_moduli_backward(const adfwi_elastic_moduli_desc* de
 
 extern "C" int adfwi_elastic_pad_forward(const adfwi_elastic_pad_desc* desc, const float* const* planes, float* const* full, void* stream)
 {
+    ADFWI_NVTX("adfwi_elastic_pad_forward");
     PdGeom g;
     int rc = pd_geom(desc, &g);
     if (rc) return rc;
@@ -190,6 +193,7 @@ extern "C" int adfwi_elastic_pad_forward(const adfwi_elastic_pad_desc* desc, con
 
 extern "C" int adfwi_elastic_pad_backward(const adfwi_elastic_pad_desc* desc, const float* const* g_full, float* const* g_planes, void* stream)
 {
+    ADFWI_NVTX("adfwi_elastic_pad_backward");
     PdGeom g;
     int rc = pd_geom(desc, &g);
     if (rc) return rc;

@@ -89,6 +89,7 @@ class ElasticFD(torch.autograd.Function):
                          n_segments, save, 0, config["shots_per_group"])
         desc.reserved[0] = 1 if config["force_generic"] else 0
         desc.reserved[1] = int(config.get("shots_per_chunk", 0))
+        desc.reserved[2] = int(config.get("shots_per_chunk_reverse", 0))
         with torch.cuda.device(dev):
             if save and config["ckpt_interval"] is None:
                 free_b, _ = torch.cuda.mem_get_info(dev)

@@ -95,6 +95,8 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if os.environ.get("ADFWI_BENCH_NO_CLOCKS"):        # diagnostics only: does the sampler itself perturb a short timed region?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -148,7 +150,7 @@ def cpu_gradient_sample(wl, ns, nt):
     sx = np.round(np.linspace(2, nx - 3, ns)).astype(np.int64); sz = np.ones(ns, np.int64)
     rx = np.round(np.linspace(0, nx - 1, wl["nr"])).astype(np.int64); rz = np.ones(wl["nr"], np.int64)
     wav = np.broadcast_to(syn.integrated_ricker(nt, wl["dt"], wl["f0"] * 4).astype(np.float32), (ns, nt)).copy()
-    O.lib().oracle_set_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1
+    O.lib().oracle_set_threads(host_cores())     # torchrun exports OMP_NUM_THREADS=1
     t0 = time.perf_counter()
     # one forward sweep (with history), residual-like cotangent from the records, one adjoint sweep
     O.acoustic_run(coef, nabc, True, wl["dt"], sx, sz, wav, rx, rz, g_rcv=lambda rec: (rec["p"], None, None),
@@ -190,7 +192,7 @@ def cpu_elastic_sample(wl, ns, nt):
     rx = np.round(np.linspace(0, nx - 1, wl["nr"])).astype(np.int64); rz = np.full(wl["nr"], z, np.int64)
     wav = np.broadcast_to(syn.integrated_ricker(nt, wl["dt"], wl["f0"] * 4).astype(np.float32), (ns, nt)).copy()
     mt = np.broadcast_to(np.eye(3, dtype=np.float32), (ns, 3, 3)).copy()
-    O.lib().oracle_set_threads(os.cpu_count() or 1)
+    O.lib().oracle_set_threads(host_cores())
     t0 = time.perf_counter()
     O.elastic_run(planes, "PML", 4, True, nz, nx, nabc, dx, dx, wl["dt"], sx, sz, wav, mt, rx, rz, bcx=bcx.astype(np.float32),
                   bcz=bcz.astype(np.float32), g_rcv=lambda rec: (None, None, None, rec["vx"], rec["vz"]))
@@ -199,10 +201,37 @@ def cpu_elastic_sample(wl, ns, nt):
     return 2.0 * cells / sec, sec
 
 
+def host_cores():
+    """Host threads the CPU legs may use: the smallest of os.cpu_count(), the scheduler affinity mask and the cgroup CPU quota.  A GPU
+    box that is a slice of a larger node can SHOW more CPUs than its quota lets run at once; an OpenMP / ATen thread team larger than
+    the quota stalls at every parallel-region barrier (seen: the unmodified reference 80x slower with 24 threads on such a slice)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                       # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:      # cgroup v1
+                q = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                per = int(f.read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def cpu_sample_size():
     """Bounded CPU sample: the oracle's adjoint parallelises over shots, so give it one shot per
     host thread (up to 16) for 50 time steps."""
-    return max(2, min(os.cpu_count() or 2, 16)), 50
+    return max(2, min(host_cores(), 16)), 50
 
 
 def cpu_port_warm(wl, reps=2):
@@ -256,7 +285,7 @@ def reference_gradient_sample(wl, ns, nt, device, reps, warmup):
     from oracle import ref_loader
     ref_loader.load()
     from ADFWI.fwi.misfit import Misfit_waveform_L2
-    torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1
+    torch.set_num_threads(host_cores())               # torchrun exports OMP_NUM_THREADS=1
     model, prop, comps = reference_objects(wl, ns, nt, device)
     fn = Misfit_waveform_L2(dt=wl["dt"])
     elastic = wl.get("kind") == "elastic"
@@ -295,7 +324,7 @@ def cpu_baseline_entry(args, wl):
         out["port"] = d.get("port")
         return out
     except Exception as e:
-        return {"value": None, "unit": "Gcell-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"cpu baseline run failed: {type(e).__name__}: {e}"[:300]}
+        return {"value": None, "unit": "Gcell-updates/s", "cores": host_cores(), "kind": "port", "sample": f"cpu baseline run failed: {type(e).__name__}: {e}"[:300]}
 
 
 def run_reference(args, wl):
@@ -307,7 +336,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     from oracle import ref_loader
-    cores = os.cpu_count()
+    cores = host_cores()
     port_v, port_s, pns, pnt = cpu_port_warm(wl, reps=max(args.steps, 1))
     port = {"value": port_v / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": "port",
             "sample": f"oracle/ C port of the reference time loop + adjoint, OpenMP over {cores} host threads, {pns} shots x {pnt} steps of the "
@@ -760,13 +789,15 @@ def run_b200_elastic(args, wl):
 
 
 SECONDARY = [
-    # (label, extra command-line arguments): short, bounded runs of the other BASELINE.json configurations, each with its own roofline
+    # (label, extra command-line arguments): short, bounded runs of the other BASELINE.json configurations, each with its own roofline.
+    # A step of the nt-400 slices lasts 50-250 ms: six timed steps, so that one host-side hiccup (seen: +10 ... +30 ms on some boxes,
+    # kernel durations unchanged, profiles/r02w_el_items.md) does not decide the line.
     ("C1 full (40 shots, nt 1600)", ["--workload", "C1", "--steps", "8"]),
-    ("C2 with the density gradient (vp + rho), nt 400 x 10 shots", ["--workload", "C2", "--rho-grad", "--nt", "400", "--shots", "10", "--batch", "10"]),
-    ("C3 iso-elastic split-PML, nt 400 x 15 shots", ["--workload", "C3", "--nt", "400", "--shots", "15", "--batch", "15"]),
-    ("C3 iso-elastic sponge (ABL), nt 400 x 15 shots", ["--workload", "C3", "--abc", "gerjan", "--nt", "400", "--shots", "15", "--batch", "15"]),
-    ("C3 iso-elastic split-PML O(2,6), nt 400 x 15 shots", ["--workload", "C3", "--order", "6", "--nt", "400", "--shots", "15", "--batch", "15"]),
-    ("C4 VTI split-PML, nt 400 x 15 shots", ["--workload", "C4", "--nt", "400", "--shots", "15", "--batch", "15"]),
+    ("C2 with the density gradient (vp + rho), nt 400 x 10 shots", ["--workload", "C2", "--rho-grad", "--nt", "400", "--shots", "10", "--batch", "10", "--steps", "6"]),
+    ("C3 iso-elastic split-PML, nt 400 x 15 shots", ["--workload", "C3", "--nt", "400", "--shots", "15", "--batch", "15", "--steps", "6"]),
+    ("C3 iso-elastic sponge (ABL), nt 400 x 15 shots", ["--workload", "C3", "--abc", "gerjan", "--nt", "400", "--shots", "15", "--batch", "15", "--steps", "6"]),
+    ("C3 iso-elastic split-PML O(2,6), nt 400 x 15 shots", ["--workload", "C3", "--order", "6", "--nt", "400", "--shots", "15", "--batch", "15", "--steps", "6"]),
+    ("C4 VTI split-PML, nt 400 x 15 shots", ["--workload", "C4", "--nt", "400", "--shots", "15", "--batch", "15", "--steps", "6"]),
     ("C5 2148x8292 slice (nt 250, 8 shots, checkpointed)", ["--workload", "C5", "--nt", "250"]),
 ]
 
@@ -816,11 +847,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false", help="skip the host-side cpu_baseline leg")
     ap.add_argument("--no-reference-cuda", dest="reference_cuda", action="store_false",
                     help="reference arm: skip timing the unmodified reference with device='cuda' beside its CPU number")
+    ap.add_argument("--cfg", action="append", default=[], metavar="KEY=INT",
+                    help="tuning experiments: override an entry of adfwi_b200.propagator.acoustic_kernels.config (e.g. shots_per_chunk=2)")
     args = ap.parse_args()
+    if args.cfg and args.impl == "b200":
+        from adfwi_b200.propagator import acoustic_kernels as _ak
+        for kv in args.cfg:
+            k, v = kv.split("=")
+            _ak.config[k] = int(v)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
     # the secondary measurements ride on the default line only (C2, full length, 1 GPU)
-    args.secondary = args.secondary and args.workload == "C2" and args.gpus == 1 and not (args.nt or args.shots or args.batch or args.rho_grad)
+    args.secondary = args.secondary and args.workload == "C2" and args.gpus == 1 and not (args.nt or args.shots or args.batch or args.rho_grad or args.cfg)
     if args.impl == "reference":
         run_reference(args, wl)
     elif wl.get("kind") == "elastic":

@@ -124,7 +124,8 @@ typedef struct {
     int32_t save_history;
     int32_t ckpt_interval;
     int32_t shots_per_group;
-    int32_t reserved[4];
+    int32_t reserved[4];     /* [0] bit 0: force the generic (unfused) kernels; [1]: shots one CTA of the fused kernels walks
+                                through per tile (0 = library picks); [2]: the same for the reverse kernels only; rest 0 */
 } adfwi_elastic_desc;
 
 size_t adfwi_elastic_workspace_bytes(const adfwi_elastic_desc* desc);

@@ -36,7 +36,7 @@ def _acoustic(dev, lo, hi):
 def _elastic(dev, lo, hi):
     from adfwi_b200 import fwi, synthetic as syn
     from adfwi_b200.propagator import ElasticPropagator
-    nz, nx, nt, dt, ns = 60, 150, 300, 1e-3, 4
+    nz, nx, nt, dt, ns = 60, 150, 1000, 1e-3, 4      # long enough for every trace to carry signal (sqrt'(0) of an all-zero residual is NaN upstream too)
     vp = syn.marmousi_like_vp(nz, nx)
     vs, rho = (vp / np.sqrt(3.0)).astype(np.float32), syn.gardner_rho(vp)
     mk = lambda a, b, c: syn.ElasticGridModel(a, b, c, dx=10.0, dz=10.0, nabc=20, free_surface=True, device=dev)
