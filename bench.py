@@ -561,7 +561,9 @@ def run_b200(args, wl):
                                 "tile walk and the working set of small grids stays in L2, so `achieved` can exceed the DRAM traffic "
                                 "actually moved (see `traffic`) and, on long tile walks, the copy-bandwidth `peak`",
                         "per_kernel_avg_ms": avg}
-        cpu_base = cpu_baseline_entry(args, wl) if args.cpu_baseline else None
+        # N = 1 only: at N > 1 the other ranks wait (spinning host threads) while rank 0 would time a thread team as wide as the box --
+        # one busy extra thread stalls every OpenMP barrier of the reference (seen: 40-80x slower at N = 2)
+        cpu_base = cpu_baseline_entry(args, wl) if (args.cpu_baseline and world == 1) else None
         line = {
             "metric": "forward+adjoint cell-updates/s (FWI gradient)", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -754,7 +756,9 @@ def run_b200_elastic(args, wl):
                     "frac_by_sweep": {"forward_recording": B_fwd * cells / (fwd * 1e-3) / 1e9 / peak,
                                       "adjoint": B_adj * cells / (adj * 1e-3) / 1e9 / peak},
                     "per_kernel_avg_ms": avg}
-        cpu_base = cpu_baseline_entry(args, wl) if args.cpu_baseline else None
+        # N = 1 only: at N > 1 the other ranks wait (spinning host threads) while rank 0 would time a thread team as wide as the box --
+        # one busy extra thread stalls every OpenMP barrier of the reference (seen: 40-80x slower at N = 2)
+        cpu_base = cpu_baseline_entry(args, wl) if (args.cpu_baseline and world == 1) else None
         if roof is not None and args.abc != "PML" and "el_fwd_fused" in avg:
             roof["note"] = ("sponge (ABL) boundary on the fused pair ela_f / ela_b: 5 unsplit fields, forward 84 B (64 + 20 recording), adjoint 84 B per "
                             "cell-update; the checkpointed row adds one plain forward sweep (64 B)")
