@@ -100,16 +100,16 @@ __device__ __forceinline__ void a_stress_cell(const EGeom& g, unsigned m, const 
         dzf_vx = zdiff<NN>(wzf, g.c);
     }
     ELF_SEQ();
-    // txx + dt*((C11*D-x vx)/dx + (C13*D-z vz)/dz), tzz, txz likewise: true divisions, see fdiv1 / DivGuard
+    // txx + dt*((C11*D-x vx)/dx + (C13*D-z vz)/dz), tzz, txz likewise: true divisions, see fdiv1 / fdiv1_tiny / DivGuard
     const float4 A0 = mul4(c11, dxb_vx), A1 = mul4(c13, dzb_vz), A2 = mul4(c13, dxb_vx), A3 = mul4(c33, dzb_vz);
     const float4 A4 = mul4(c55, dxf_vz), A5 = mul4(c55, dzf_vx);
     DivGuard dg;
     dg.add(A0); dg.add(A1); dg.add(A2); dg.add(A3); dg.add(A4); dg.add(A5);
     float4 t0 = fdivs(A0, g.dx, g.rdx), t1 = fdivs(A1, g.dz, g.rdz), t2 = fdivs(A2, g.dx, g.rdx);
     float4 t3 = fdivs(A3, g.dz, g.rdz), t4 = fdivs(A4, g.dx, g.rdx), t5 = fdivs(A5, g.dz, g.rdz);
-    if (!dg.ok()) {          // rare: a numerator in the underflow range -> the IEEE sequence
-        t0 = ieee_divs(A0, g.dx); t1 = ieee_divs(A1, g.dz); t2 = ieee_divs(A2, g.dx);
-        t3 = ieee_divs(A3, g.dz); t4 = ieee_divs(A4, g.dx); t5 = ieee_divs(A5, g.dz);
+    if (!dg.ok()) {          // a numerator in the underflow range (the band ahead of a wavefront): scaled sequence
+        t0 = safe_divs(A0, g.dx, g.rdx); t1 = safe_divs(A1, g.dz, g.rdz); t2 = safe_divs(A2, g.dx, g.rdx);
+        t3 = safe_divs(A3, g.dz, g.rdz); t4 = safe_divs(A4, g.dx, g.rdx); t5 = safe_divs(A5, g.dz, g.rdz);
     }
     const float4 n0 = add4(sp[0], smul(g.dt, add4(t0, t1)));
     const float4 n1 = add4(sp[1], smul(g.dt, add4(t2, t3)));
@@ -273,8 +273,8 @@ __device__ __forceinline__ void af_tile(const CUtensorMap* th, const CUtensorMap
             float4 ex = add4(fdivs(dxf_txx, g.dx, g.rdx), fdivs(dzb_txz, g.dz, g.rdz));      // D+x txx/dx + D-z txz/dz
             float4 ez = add4(fdivs(dxb_txz, g.dx, g.rdx), fdivs(dzf_tzz, g.dz, g.rdz));      // D-x txz/dx + D+z tzz/dz
             if (!dg.ok()) {
-                ex = add4(ieee_divs(dxf_txx, g.dx), ieee_divs(dzb_txz, g.dz));
-                ez = add4(ieee_divs(dxb_txz, g.dx), ieee_divs(dzf_tzz, g.dz));
+                ex = add4(safe_divs(dxf_txx, g.dx, g.rdx), safe_divs(dzb_txz, g.dz, g.rdz));
+                ez = add4(safe_divs(dxb_txz, g.dx, g.rdx), safe_divs(dzf_tzz, g.dz, g.rdz));
             }
             const float4 ux = sel4(mt_, add4(q0, mul4(DBX, ex)), q0);        // undamped new velocities (:749-750)
             const float4 uz = sel4(mt_, add4(q1, mul4(DBZ, ez)), q1);

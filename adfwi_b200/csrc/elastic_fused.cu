@@ -157,7 +157,7 @@ __device__ __forceinline__ float4 smul(float s, const float4& a) { return make_f
 // reference -- at 5 instructions and with no slow path for zero numerators (the compiler's division sequence
 // takes its out-of-line path for every zero operand, i.e. for every cell the wave has not reached yet).
 // The remainders are exact only away from the underflow range: non-zero numerators below 2^-100 in magnitude
-// take the IEEE division (DivGuard).  Divisors are grid spacings and 1 + dt/2*profile (moderate magnitudes).
+// take the scaled sequence fdiv1_tiny (DivGuard).  Divisors are grid spacings and 1 + dt/2*profile (moderate magnitudes).
 __device__ __forceinline__ float fdiv1(float a, float b, float rb)
 {
     float q = a * rb;
@@ -178,12 +178,34 @@ struct DivGuard {
     }
     __device__ __forceinline__ bool ok() const { return mn >= ((27u << 24) - 1u); }
 };
-__device__ __noinline__ float4 ieee_div4(float4 a, float4 b)      // rare path, kept out of line (code size)
+// RN(a/b) for |a| < 2^-100 (zero and denormals included), b > 0 of moderate magnitude, rb = RN(1/b) -- the numerators of the band
+// ahead of every wavefront, where the field decays through the underflow range.  The compiler's IEEE division takes its slowest
+// out-of-line path for exactly these operands (ncu: 11 % of all executed instructions of ela_f on an expanding wavefield).  Here:
+// scale the numerator by 2^80 (exact), take the Markstein quotient q = RN(2^80 a / b) with its exact remainder r, scale back.
+// t = RN(q 2^-80) is exact when the result is normal; when it is denormal it is the correct rounding of a/b unless q sits exactly
+// on a rounding boundary of the denormal grid (|q - t 2^80| = 2^-70) while a/b does not (r != 0): then the true quotient lies on
+// the side of r, and the hardware's ties-to-even choice is moved by one denormal step when it went the other way.  Checked
+// bit for bit against the IEEE division on 3.2e8 operand pairs (ties, denormal numerators, denormal quotients).
+__device__ __forceinline__ float fdiv1_tiny(float a, float b, float rb)
 {
-    return make_float4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w);
+    const float a2 = a * 0x1p80f;
+    float q = a2 * rb;
+    q = __fmaf_rn(__fmaf_rn(-b, q, a2), rb, q);
+    q = __fmaf_rn(__fmaf_rn(-b, q, a2), rb, q);
+    const float r = __fmaf_rn(-b, q, a2);
+    float t = q * 0x1p-80f;
+    const float e = __fmaf_rn(-t, 0x1p80f, q);
+    if (fabsf(e) == 0x1p-70f && r != 0.f && ((r > 0.f) == (e > 0.f))) t += copysignf(0x1p-149f, e);
+    return t;
 }
-__device__ __forceinline__ float4 ieee_divs(const float4& a, float b) { return ieee_div4(a, make_float4(b, b, b, b)); }
-// unguarded fast divisions: the caller adds the numerator to a DivGuard and redoes the work with ieee_div4 when !ok()
+__device__ __forceinline__ float fdiv1_any(float a, float b, float rb) { return fabsf(a) < 0x1p-100f ? fdiv1_tiny(a, b, rb) : fdiv1(a, b, rb); }
+// the guarded path of the forward kernels, kept out of line (code size, registers): correctly rounded for every numerator
+__device__ __noinline__ float4 safe_div4(float4 a, float4 b, float4 rb)
+{
+    return make_float4(fdiv1_any(a.x, b.x, rb.x), fdiv1_any(a.y, b.y, rb.y), fdiv1_any(a.z, b.z, rb.z), fdiv1_any(a.w, b.w, rb.w));
+}
+__device__ __forceinline__ float4 safe_divs(const float4& a, float b, float rb) { return safe_div4(a, make_float4(b, b, b, b), make_float4(rb, rb, rb, rb)); }
+// unguarded fast divisions: the caller adds the numerator to a DivGuard and redoes the work with safe_div4 when !ok()
 __device__ __forceinline__ float4 fdiv4(const float4& a, const float4& b, const float4& rb)
 {
     return make_float4(fdiv1(a.x, b.x, rb.x), fdiv1(a.y, b.y, rb.y), fdiv1(a.z, b.z, rb.z), fdiv1(a.w, b.w, rb.w));
@@ -618,11 +640,11 @@ __device__ __forceinline__ void v_tile(const CUtensorMap* th, const CUtensorMap*
                 } else {
                     n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
                 }
-                if (!dg.ok()) {          // rare: a numerator in the underflow range -> the IEEE sequence
-                    t0 = ieee_divs(A0, g.dx); t1 = ieee_divs(A1, g.dz); t2 = ieee_divs(A2, g.dx); t3 = ieee_divs(A3, g.dz);
+                if (!dg.ok()) {          // a numerator in the underflow range (the band ahead of a wavefront): scaled sequence
+                    t0 = safe_divs(A0, g.dx, g.rdx); t1 = safe_divs(A1, g.dz, g.rdz); t2 = safe_divs(A2, g.dx, g.rdx); t3 = safe_divs(A3, g.dz, g.rdz);
                     if (PML) {
-                        n0 = ieee_div4(add4(mul4(PXN[j], q0), t0), PXD[j]); n1 = ieee_div4(add4(mul4(PZN[j], q1), t1), PZD[j]);
-                        n2 = ieee_div4(add4(mul4(PXN[j], q2), t2), PXD[j]); n3 = ieee_div4(add4(mul4(PZN[j], q3), t3), PZD[j]);
+                        n0 = safe_div4(add4(mul4(PXN[j], q0), t0), PXD[j], RPXD[j]); n1 = safe_div4(add4(mul4(PZN[j], q1), t1), PZD[j], RPZD[j]);
+                        n2 = safe_div4(add4(mul4(PXN[j], q2), t2), PXD[j], RPXD[j]); n3 = safe_div4(add4(mul4(PZN[j], q3), t3), PZD[j], RPZD[j]);
                     } else {
                         n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
                     }
@@ -1003,11 +1025,12 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
                     n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
                 }
                 if (!dg.ok()) {
-                    t0 = ieee_divs(A0, g.dx); t1 = ieee_divs(A1, g.dz); t2 = ieee_divs(A2, g.dx); t3 = ieee_divs(A3, g.dz);
+                    t0 = safe_divs(A0, g.dx, g.rdx); t1 = safe_divs(A1, g.dz, g.rdz); t2 = safe_divs(A2, g.dx, g.rdx); t3 = safe_divs(A3, g.dz, g.rdz);
                     if (PML) {
                         const float4 pxn = sub4(one4(), HBX[j]), pzn = sub4(one4(), HBZ[j]), pxd = add4(one4(), HBX[j]), pzd = add4(one4(), HBZ[j]);
-                        n0 = ieee_div4(add4(mul4(pxn, q0), t0), pxd); n1 = ieee_div4(add4(mul4(pzn, q1), t1), pzd);
-                        n2 = ieee_div4(add4(mul4(pxn, q2), t2), pxd); n3 = ieee_div4(add4(mul4(pzn, q3), t3), pzd);
+                        const float4 pxi = rcp4(pxd), pzi = rcp4(pzd);
+                        n0 = safe_div4(add4(mul4(pxn, q0), t0), pxd, pxi); n1 = safe_div4(add4(mul4(pzn, q1), t1), pzd, pzi);
+                        n2 = safe_div4(add4(mul4(pxn, q2), t2), pxd, pxi); n3 = safe_div4(add4(mul4(pzn, q3), t3), pzd, pzi);
                     } else {
                         n0 = add4(q0, t0); n1 = add4(q1, t1); n2 = add4(q2, t2); n3 = add4(q3, t3);
                     }
