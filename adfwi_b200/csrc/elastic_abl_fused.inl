@@ -39,6 +39,10 @@ template <int NN> struct GeoA {
     static constexpr int W2 = NG + 2 * GX2;
     static constexpr int NRING2 = 4 * NN * W2 + TZ * 2 * GX2;  // float4 groups of the 2NN ring (same enumeration as GeoB)
     static constexpr int FS_BYTES = 2 * G::RX2 * 4;            // reverse kernel: free-surface addends of rows h-1 (vz) and h (vx)
+    // forward kernel: C11, C13, C33, C55 of the ring cells, filled once per (tile, chunk) by the thread that reads them every shot
+    // (float4 SoA).  ela_f 0.80 -> 0.83 of its roofline; the same tables bought nothing in ela_b and cost elf_f 1 % (its two CTAs
+    // already take 217 KB of the SM's shared memory), so those two keep reading the L2-resident pack (profiles/r02x_el_forward.md)
+    static constexpr int TF_BYTES = 4 * G::NRING * 16;
 };
 
 template <int NN> __device__ __forceinline__ void a_issue(const Cursor& c, unsigned char* smem, uint64_t* bar, int k,
@@ -122,12 +126,13 @@ __device__ __forceinline__ void a_stress_cell(const EGeom& g, unsigned m, const 
 template <int NN, bool FS, bool SAVE>
 __device__ __forceinline__ void af_tile(const CUtensorMap* th, const CUtensorMap* th2, const EGeom& g, const AFArgs& a,
                                         unsigned char* smem, uint64_t* bar, uint32_t& par, int& stage, Cursor& pc, int* ring,
-                                        int* s_sz, int* s_sx, float* s_sxx, float* s_szz, float* s_sxz,
+                                        int* s_sz, int* s_sx, float* s_sxx, float* s_szz, float* s_sxz, float4* tab,
                                         const Roles& R, int tid, int tile, int s_lo, int s_hi, bool first)
 {
     using G = Geo<NN>;
     constexpr int RX2 = G::RX2, HX2 = G::HX2, HQ = G::HB / 4, HQ2 = G::HB2 / 4;
     const uint64_t pol = l2_keep_policy();
+    float4* T_c11 = tab; float4* T_c13 = tab + G::NRING; float4* T_c33 = tab + 2 * G::NRING; float4* T_c55 = tab + 3 * G::NRING;
     const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
     const int X0 = txi * TX, Z0 = tzi * TZ;
     const int gx = X0 + R.c0, gz = Z0 + R.r0;
@@ -148,8 +153,15 @@ __device__ __forceinline__ void af_tile(const CUtensorMap* th, const CUtensorMap
     const float4 C11 = ldk4(a.cp.c11 + oc, pol), C13 = ldk4(a.cp.c13 + oc, pol), C33 = ldk4(a.cp.c33 + oc, pol), C55 = ldk4(a.cp.c55 + oc, pol);
     const float4 DBX = smul(g.dt, ldk4(a.cp.bx + oc, pol)), DBZ = smul(g.dt, ldk4(a.cp.bz + oc, pol));     // dt*bx, dt*bz (:749-750)
     const float4 DMP = ldk4(a.cp.bcx + oc, pol);                                                              // sponge plane
+    for (int i = tid; i < G::NRING; i += NTH) {          // ring coefficients: written and read by the same thread (no barrier needed)
+        int r, gi;
+        ring_cell<NN>(i, r, gi);
+        const ptrdiff_t o = (ptrdiff_t)(Z0 + r) * g.cpld + X0 + 4 * gi;
+        T_c11[i] = ldk4(a.cp.c11 + o, pol); T_c13[i] = ldk4(a.cp.c13 + o, pol); T_c33[i] = ldk4(a.cp.c33 + o, pol); T_c55[i] = ldk4(a.cp.c55 + o, pol);
+    }
     const int rcv_lo = a.nr > 0 ? a.rb.start[tile] : 0, rcv_hi = a.nr > 0 ? a.rb.start[tile + 1] : 0;
     const bool has_rcv = rcv_hi > rcv_lo;
+    const bool producer = tid == NTH - 32;              // lane 0 of the last warp, which has no ring cells
     const int hv = (R.r0 + 2 * NN) * RX2 + R.c0 + HX2, hs = (R.r0 + NN) * RXH + R.c0 + HX;
     // side buffer of the free-surface rows: [parity][row: 0 = undamped vz[h-1], 1 = undamped vx[h]][shot][ld]
     const size_t side_row = (size_t)g.ns * g.ld;
@@ -159,7 +171,7 @@ __device__ __forceinline__ void af_tile(const CUtensorMap* th, const CUtensorMap
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (tid == 0 && pc.valid) { a_issue<NN>(pc, smem, bar, k, th, th2, g.ns, rbase); pc.next(g, a.w, ring); }
+            if (producer && pc.valid) { a_issue<NN>(pc, smem, bar, k, th, th2, g.ns, rbase); pc.next(g, a.w, ring); }
     }
     __syncthreads();
 
@@ -216,10 +228,9 @@ __device__ __forceinline__ void af_tile(const CUtensorMap* th, const CUtensorMap
             const int gzr = Z0 + r, gxr = X0 + 4 * gi;
             const int hv2 = (r + 2 * NN) * RX2 + 4 * gi + HX2, hs2 = (r + NN) * RXH + 4 * gi + HX;
             const unsigned m = row_in<NN>(gzr, g.nzp) ? col_mask<NN>(gxr, g.nxp) : 0u;
-            const ptrdiff_t o = (ptrdiff_t)gzr * g.cpld + gxr;
             float4 sp[3], d[3];
             sp[0] = ld4(txx + hs2); sp[1] = ld4(tzz + hs2); sp[2] = ld4(txz + hs2);
-            a_stress_cell<NN>(g, m, vx, vz, hv2, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol), ldk4(a.cp.c55 + o, pol), d);
+            a_stress_cell<NN>(g, m, vx, vz, hv2, sp, T_c11[i], T_c13[i], T_c33[i], T_c55[i], d);
             if (szs == gzr && !(FS && gzr < NN)) {
                 const int dc = sxs - gxr;
                 if (dc >= 0 && dc < 4) { addc4(sp[0], dc, sxx); addc4(sp[1], dc, szz); addc4(sp[2], dc, sxz); }
@@ -310,8 +321,14 @@ __device__ __forceinline__ void af_tile(const CUtensorMap* th, const CUtensorMap
             }
         }
         fence_proxy_async();
-        __syncthreads();
-        if (tid == 0 && pc.valid) { a_issue<NN>(pc, smem, bar, k, th, th2, g.ns, rbase); pc.next(g, a.w, ring); }
+        // stage k has been consumed: refill it with the shot after the next.  Only the producer's warp waits for the other warps'
+        // phase B (named barrier 1); they go straight on to the next shot, which lives in the other stage
+        if (tid >= NTH - 32) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory");
+            if (producer && pc.valid) { a_issue<NN>(pc, smem, bar, k, th, th2, g.ns, rbase); pc.next(g, a.w, ring); }
+        } else {
+            asm volatile("bar.arrive 1, %0;" ::"n"(NTH) : "memory");
+        }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
 }
@@ -328,6 +345,7 @@ ela_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     float* s_sxx = (float*)(s_sx + CMAX);
     float* s_szz = s_sxx + CMAX;
     float* s_sxz = s_szz + CMAX;
+    float4* tab = (float4*)(smem + NSTAGE * GeoA<NN>::STAGE + TAIL_BYTES);
     const int tid = threadIdx.x;
     if (tid == 0) { for (int k = 0; k < NSTAGE; ++k) mbar_init(bar + k, 1); }
     __syncthreads();
@@ -346,7 +364,7 @@ ela_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
         const int tile = item / a.w.nchunks, chunk = item - tile * a.w.nchunks;
         const int s_lo = a.w.s_begin + chunk * a.w.chunk;
         const int s_hi = min(s_lo + a.w.chunk, a.w.s_end);
-        af_tile<NN, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, R, tid, tile, s_lo, s_hi, first);
+        af_tile<NN, FS, SAVE>(&th, &th2, g, a, smem, bar, par, stage, pc, ring, s_sz, s_sx, s_sxx, s_szz, s_sxz, tab, R, tid, tile, s_lo, s_hi, first);
         __syncthreads();
     }
 }
@@ -391,11 +409,12 @@ __device__ __forceinline__ void ab_tile(const CUtensorMap* th, const CUtensorMap
     float4 G11 = zero4(), G13 = zero4(), G33 = zero4(), G55 = zero4(), GBX = zero4(), GBZ = zero4();
     const bool have_g = a.nr > 0 && (a.g[0] || a.g[1] || a.g[2] || a.g[3] || a.g[4]);
     const bool inject = have_g && a.rb.nbr[tile];
+    const bool producer = tid == NTH - 32;              // lane 0 of the last warp
     if (first) {
         griddep_wait();
 #pragma unroll
         for (int k = 0; k < NSTAGE; ++k)
-            if (tid == 0 && pc.valid) { ab_issue<NN>(pc, smem, bar, k, th, th2, thh, g.ns, rbase, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+            if (producer && pc.valid) { ab_issue<NN>(pc, smem, bar, k, th, th2, thh, g.ns, rbase, a.hist_len, a.tl); pc.next(g, a.w, ring); }
     }
     __syncthreads();
 
@@ -586,8 +605,13 @@ __device__ __forceinline__ void ab_tile(const CUtensorMap* th, const CUtensorMap
             }
         }
         fence_proxy_async();
-        __syncthreads();
-        if (tid == 0 && pc.valid) { ab_issue<NN>(pc, smem, bar, k, th, th2, thh, g.ns, rbase, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+        // as in ela_f: only the producer's warp waits for the other warps' phase D before it refills stage k
+        if (tid >= NTH - 32) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory");
+            if (producer && pc.valid) { ab_issue<NN>(pc, smem, bar, k, th, th2, thh, g.ns, rbase, a.hist_len, a.tl); pc.next(g, a.w, ring); }
+        } else {
+            asm volatile("bar.arrive 1, %0;" ::"n"(NTH) : "memory");
+        }
         stage = (stage + 1 == NSTAGE) ? 0 : stage + 1;
     }
     if (cell_ok) {

@@ -947,7 +947,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
             if (PML) {
                 const float4 bx_ = ldk4(a.cp.bcx + o, pol), bz_ = ldk4(a.cp.bcz + o, pol);
                 pxn = sub4(one4(), smul(g.half_dt, bx_)); pzn = sub4(one4(), smul(g.half_dt, bz_));
-                pxi = div4(one4(), add4(one4(), smul(g.half_dt, bx_))); pzi = div4(one4(), add4(one4(), smul(g.half_dt, bz_)));
+                pxi = rcp4(add4(one4(), smul(g.half_dt, bx_))); pzi = rcp4(add4(one4(), smul(g.half_dt, bz_)));
             }
             float4 sp[6], d[4];
             f_stress_cell<NN, PML>(g, m, vxx, vxz, vzx, vzz, hv, ssp + hs, nullptr, 0u, sp, ldk4(a.cp.c11 + o, pol), ldk4(a.cp.c13 + o, pol), ldk4(a.cp.c33 + o, pol),
@@ -1070,7 +1070,7 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
             }
         }
         if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
-        __syncthreads();
+        __syncthreads();               // a full barrier: the stress sums are single-buffered, phase A of the next shot overwrites what phase B reads
         if (producer && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, ctl[2] & 1, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
         ctl[2] = ctl[2] + 1;
     }
@@ -2751,7 +2751,7 @@ int ela_make_maps(const EAPlan& P, EAMaps* M)
     return make_tmap_f32(&M->hist, P.hist, 3, g.nxp, g.ld, g.nzp, (uint64_t)P.ns * P.K * ANHIST, TX, TZ);
 }
 
-template <int NN> constexpr int af_smem() { return NSTAGE * GeoA<NN>::STAGE + TAIL_BYTES; }
+template <int NN> constexpr int af_smem() { return NSTAGE * GeoA<NN>::STAGE + TAIL_BYTES + GeoA<NN>::TF_BYTES; }
 template <int NN> constexpr int ab_smem() { return NSTAGE * GeoA<NN>::STAGE + TAIL_SMALL + GeoA<NN>::FS_BYTES + 64; }
 static_assert(2 * (af_smem<3>() + 1024) <= 233472 && 2 * (ab_smem<3>() + 1024) <= 233472, "two CTAs per SM must fit in shared memory");
 
