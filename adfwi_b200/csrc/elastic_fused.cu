@@ -828,7 +828,8 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
     // loop control of the shot walk lives in the warp's slot of shared memory (ctl[0] = first shot, ctl[1] = end,
     // ctl[2] = shots this CTA has processed): at the 128-register cap the compiler spills exactly these, and a spilled
     // value comes back at L2 latency on the critical path of every shot
-    ctl[0] = s_lo; ctl[1] = s_hi;
+    if ((tid & 31) == 0) { ctl[0] = s_lo; ctl[1] = s_hi; }      // one writer per warp slot (all lanes hold the same values)
+    __syncwarp();
     const uint64_t pol = l2_keep_policy();
     const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
     const int X0 = txi * TX, Z0 = tzi * TZ;
@@ -1072,7 +1073,9 @@ __device__ __forceinline__ void f_tile(const CUtensorMap* th, const CUtensorMap*
         if (has_rcv || (FS && tzi == 0)) fence_proxy_async();
         __syncthreads();               // a full barrier: the stress sums are single-buffered, phase A of the next shot overwrites what phase B reads
         if (producer && pcv.valid) { f_issue_v<NN>(pcv, smem, bar, ctl[2] & 1, th2, g.ns, rbase); pcv.next(g, a.w, ring); }
-        ctl[2] = ctl[2] + 1;
+        __syncwarp();
+        if ((tid & 31) == 0) ctl[2] = ctl[2] + 1;
+        __syncwarp();
     }
 }
 
@@ -1094,7 +1097,8 @@ elf_f(const __grid_constant__ CUtensorMap th, const __grid_constant__ CUtensorMa
     const Roles R(tid);
     static_assert(NSTAGE == 2, "f_tile derives stage and barrier parities from the shot counter");
     volatile int* ctl = (volatile int*)(smem + G::F_SMEM + TAIL_BYTES) + (tid >> 5) * 4;
-    ctl[2] = 0;
+    if ((tid & 31) == 0) ctl[2] = 0;
+    __syncwarp();
     const int nitems = g.ntx * g.ntz * a.w.nchunks;
     int* ring = (int*)(bar + 4);
     // the two producer cursors live in shared memory: only one thread uses them, registers are scarce

@@ -2,7 +2,8 @@
 was <= 64 x 88 cells and nt <= 260, where the fused kernels run 1-4 tiles and the adjoint round-off has not grown yet).
 
   * CUDA path vs the CPU oracle on the C1 grid IN FULL (148 x 260 padded, nt 1600, 4 shots) and on 2-shot x 400-step
-    slices of the C2 (450 x 1800), C3 (402 x 1800, iso-elastic split-PML) and C4 (372 x 820, VTI) grids: records
+    slices of the C2 (450 x 1800), C3 (402 x 1800, iso-elastic split-PML) and C4 (372 x 820, VTI) grids and a 1-shot x 40-step
+    slice of the C5 grid (2148 x 8292): records
     bit-identical, coefficient-plane gradients and model-level gradients (vp, rho / vp, vs, rho / eps, delta) within the
     1e-4 bar of BASELINE.json, with a realistic cotangent (L2 waveform misfit against records of a "true" model);
   * CUDA path vs committed fixtures of the UNMODIFIED reference at its examples' own grid size and nt
@@ -96,6 +97,15 @@ def test_c1_full_vs_oracle():
 def test_c2_slice_vs_oracle():
     """C2 = 350 x 1700 (+50 -> 450 x 1800), dx 10 m, dt 1 ms: 2 shots x 400 steps (f0 raised so that the wave has left the source)."""
     _acoustic_vs_oracle(350, 1700, 50, 400, 10.0, 1e-3, 25.0, ns=2, nr=1700, tag="C2 grid slice (nt 400, 2 shots)")
+
+
+def test_c5_slice_vs_oracle():
+    """C5 = 2048 x 8192 (+50 -> 2148 x 8292, 4422 tiles of 64 x 32), dx 5 m, dt 0.5 ms: 1 shot x 40 steps (the oracle keeps its
+    history in host memory: 8.5 GB for this slice)."""
+    import psutil
+    if psutil.virtual_memory().available < 40 * 2 ** 30:
+        pytest.skip("needs 40 GB of free host memory for the oracle's history")
+    _acoustic_vs_oracle(2048, 8192, 50, 40, 5.0, 5e-4, 100.0, ns=1, nr=2048, tag="C5 grid slice (nt 40, 1 shot)")
 
 
 # ---------------------------------------------------------------------------------------------------
