@@ -471,13 +471,17 @@ def run_b200(args, wl):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         trace = [time.perf_counter()]
+        st0 = torch.cuda.memory_stats(dev) if os.environ.get("ADFWI_BENCH_TRACE") else None
         for _ in range(steps):
             fn()
             trace.append(time.perf_counter())
         e1.record()
         barrier()
-        if os.environ.get("ADFWI_BENCH_TRACE"):      # diagnostics: host-side time at which each step's calls returned
-            sys.stderr.write(f"[trace] {fn.__name__}: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(trace, trace[1:])) + " ms\n")
+        if st0 is not None:      # diagnostics: host-side time at which each step's calls returned; allocator traffic to the driver
+            st1 = torch.cuda.memory_stats(dev)
+            keys = ("num_device_alloc", "num_device_free", "num_alloc_retries", "num_ooms")
+            sys.stderr.write(f"[trace] {fn.__name__}: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(trace, trace[1:])) + " ms; " +
+                             ", ".join(f"{k} +{st1.get(k, 0) - st0.get(k, 0)}" for k in keys) + "\n")
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -691,13 +695,17 @@ def run_b200_elastic(args, wl):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         trace = [time.perf_counter()]
+        st0 = torch.cuda.memory_stats(dev) if os.environ.get("ADFWI_BENCH_TRACE") else None
         for _ in range(steps):
             fn()
             trace.append(time.perf_counter())
         e1.record()
         barrier()
-        if os.environ.get("ADFWI_BENCH_TRACE"):      # diagnostics: host-side time at which each step's calls returned
-            sys.stderr.write(f"[trace] {fn.__name__}: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(trace, trace[1:])) + " ms\n")
+        if st0 is not None:      # diagnostics: host-side time at which each step's calls returned; allocator traffic to the driver
+            st1 = torch.cuda.memory_stats(dev)
+            keys = ("num_device_alloc", "num_device_free", "num_alloc_retries", "num_ooms")
+            sys.stderr.write(f"[trace] {fn.__name__}: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(trace, trace[1:])) + " ms; " +
+                             ", ".join(f"{k} +{st1.get(k, 0) - st0.get(k, 0)}" for k in keys) + "\n")
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
