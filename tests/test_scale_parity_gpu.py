@@ -116,7 +116,7 @@ COMPS = ("txx", "tzz", "txz", "vx", "vz")
 COEF_IDX = {"C11": 0, "C13": 2, "C33": 11, "C55": 18}
 
 
-def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, tag):
+def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, tag, abc="PML"):
     from adfwi_b200 import synthetic as syn
     from adfwi_b200.propagator import ElasticPropagator, elastic_kernels as ek
     O = _oracle_threads()
@@ -130,11 +130,15 @@ def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, 
         eps_true[nz // 3:nz // 2, nx // 3:nx // 2] = 0.2
     survey = syn.surface_survey(nx, ns, nr, nt, dt, f0, src_z=z_sr, rcv_z=z_sr)
     mk = lambda v, e, req, d: syn.ElasticGridModel(v, mk_vs(v), syn.gardner_rho(v), eps=e, delta=delta, dx=dx, dz=dx, nabc=nabc,
-                                                   free_surface=True, abc_type="PML", requires_grad=req, device=d)
+                                                   free_surface=True, abc_type=abc, requires_grad=req, device=d)
     true_model, model = mk(vp_true, eps_true, (), dev), mk(vp0, eps, params, dev)
     prop_true = ElasticPropagator(true_model, survey, device=dev)
     prop = ElasticPropagator(model, survey, device=dev)
-    prop.bcx, prop.bcz = prop_true.bcx, prop_true.bcz
+    pml = abc == "PML"
+    if pml:
+        prop.bcx, prop.bcz = prop_true.bcx, prop_true.bcz
+    else:
+        prop.damp = prop_true.damp
     with torch.no_grad():
         o = prop_true.forward()
         obs = {c: o[c] for c in ("vx", "vz")}
@@ -152,17 +156,17 @@ def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, 
     for k, i in COEF_IDX.items():
         CC[i] = L[k]
     rec2 = ek.forward_kernel(nx, nz, dx, dx, nt, dt, nabc, True, prop.src_x, prop.src_z, ns, prop.wavelet, prop.moment_tensor,
-                             prop.rcv_x, prop.rcv_z, nr, "PML", prop.bcx, prop.bcz, None, None, None, L["bx"], L["bz"], CC,
-                             fd_order=4, n_segments=1, device=dev)
+                             prop.rcv_x, prop.rcv_z, nr, abc, prop.bcx if pml else None, prop.bcz if pml else None, None if pml else prop.damp,
+                             None, None, L["bx"], L["bz"], CC, fd_order=4, n_segments=1, device=dev)
     for c in COMPS:
         assert torch.equal(rec2[c], rec[c]), c
     ((rec2["vx"] * g_vx).sum() + (rec2["vz"] * g_vz).sum()).backward()
     # oracle on the same planes and the same cotangent
     planes = {k: L[k].detach().cpu().numpy() for k in PLANES}
     src = survey.source
-    ref = O.elastic_run(planes, "PML", 4, True, nz, nx, nabc, dx, dx, dt, src.loc[:, 0], src.loc[:, 1], src.wavelet, src.moment_tensor,
-                        survey.receiver.loc[:, 0], survey.receiver.loc[:, 1], bcx=prop.bcx.cpu().numpy(), bcz=prop.bcz.cpu().numpy(),
-                        g_rcv=[None, None, None, g_vx.cpu().numpy(), g_vz.cpu().numpy()])
+    bc = dict(bcx=prop.bcx.cpu().numpy(), bcz=prop.bcz.cpu().numpy()) if pml else dict(damp=prop.damp.cpu().numpy())
+    ref = O.elastic_run(planes, abc, 4, True, nz, nx, nabc, dx, dx, dt, src.loc[:, 0], src.loc[:, 1], src.wavelet, src.moment_tensor,
+                        survey.receiver.loc[:, 0], survey.receiver.loc[:, 1], g_rcv=[None, None, None, g_vx.cpu().numpy(), g_vz.cpu().numpy()], **bc)
     for c in COMPS:
         got = rec[c].detach().cpu().numpy()
         assert rel_l2(got, ref[c]) <= REC_TOL, (tag, c)
@@ -184,6 +188,12 @@ def test_c3_slice_vs_oracle():
     """C3 = iso-elastic 350 x 1700 (+50, free surface -> 402 x 1800), split-PML O(2,4): 2 shots x 400 steps, vp / vs / rho."""
     _elastic_vs_oracle(350, 1700, 50, 400, 10.0, 1e-3, 25.0, ns=2, nr=1700, z_sr=10, vti=False, params=("vp", "vs", "rho"),
                        tag="C3 grid slice (nt 400, 2 shots)")
+
+
+def test_c3_sponge_slice_vs_oracle():
+    """The C3 grid with the multiplicative sponge (ABL) boundary: the fused pair ela_f / ela_b, 2 shots x 400 steps."""
+    _elastic_vs_oracle(350, 1700, 50, 400, 10.0, 1e-3, 25.0, ns=2, nr=1700, z_sr=10, vti=False, params=("vp", "vs", "rho"),
+                       tag="C3 grid slice, sponge boundary (nt 400, 2 shots)", abc="gerjan")
 
 
 def test_c4_slice_vs_oracle():
