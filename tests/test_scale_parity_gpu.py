@@ -116,7 +116,7 @@ COMPS = ("txx", "tzz", "txz", "vx", "vz")
 COEF_IDX = {"C11": 0, "C13": 2, "C33": 11, "C55": 18}
 
 
-def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, tag, abc="PML"):
+def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, tag, abc="PML", order=4):
     from adfwi_b200 import synthetic as syn
     from adfwi_b200.propagator import ElasticPropagator, elastic_kernels as ek
     O = _oracle_threads()
@@ -140,10 +140,10 @@ def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, 
     else:
         prop.damp = prop_true.damp
     with torch.no_grad():
-        o = prop_true.forward()
+        o = prop_true.forward(fd_order=order)
         obs = {c: o[c] for c in ("vx", "vz")}
     # model-level gradients through the propagator + parameterisation
-    rec = prop.forward()
+    rec = prop.forward(fd_order=order)
     loss = l2_misfit(rec["vx"], obs["vx"], dt) + l2_misfit(rec["vz"], obs["vz"], dt)
     g_vx, g_vz = torch.autograd.grad(loss, [rec["vx"], rec["vz"]], retain_graph=True)
     loss.backward()
@@ -157,7 +157,7 @@ def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, 
         CC[i] = L[k]
     rec2 = ek.forward_kernel(nx, nz, dx, dx, nt, dt, nabc, True, prop.src_x, prop.src_z, ns, prop.wavelet, prop.moment_tensor,
                              prop.rcv_x, prop.rcv_z, nr, abc, prop.bcx if pml else None, prop.bcz if pml else None, None if pml else prop.damp,
-                             None, None, L["bx"], L["bz"], CC, fd_order=4, n_segments=1, device=dev)
+                             None, None, L["bx"], L["bz"], CC, fd_order=order, n_segments=1, device=dev)
     for c in COMPS:
         assert torch.equal(rec2[c], rec[c]), c
     ((rec2["vx"] * g_vx).sum() + (rec2["vz"] * g_vz).sum()).backward()
@@ -165,7 +165,7 @@ def _elastic_vs_oracle(nz, nx, nabc, nt, dx, dt, f0, ns, nr, z_sr, vti, params, 
     planes = {k: L[k].detach().cpu().numpy() for k in PLANES}
     src = survey.source
     bc = dict(bcx=prop.bcx.cpu().numpy(), bcz=prop.bcz.cpu().numpy()) if pml else dict(damp=prop.damp.cpu().numpy())
-    ref = O.elastic_run(planes, abc, 4, True, nz, nx, nabc, dx, dx, dt, src.loc[:, 0], src.loc[:, 1], src.wavelet, src.moment_tensor,
+    ref = O.elastic_run(planes, abc, order, True, nz, nx, nabc, dx, dx, dt, src.loc[:, 0], src.loc[:, 1], src.wavelet, src.moment_tensor,
                         survey.receiver.loc[:, 0], survey.receiver.loc[:, 1], g_rcv=[None, None, None, g_vx.cpu().numpy(), g_vz.cpu().numpy()], **bc)
     for c in COMPS:
         got = rec[c].detach().cpu().numpy()
@@ -194,6 +194,12 @@ def test_c3_sponge_slice_vs_oracle():
     """The C3 grid with the multiplicative sponge (ABL) boundary: the fused pair ela_f / ela_b, 2 shots x 400 steps."""
     _elastic_vs_oracle(350, 1700, 50, 400, 10.0, 1e-3, 25.0, ns=2, nr=1700, z_sr=10, vti=False, params=("vp", "vs", "rho"),
                        tag="C3 grid slice, sponge boundary (nt 400, 2 shots)", abc="gerjan")
+
+
+def test_c3_o26_slice_vs_oracle():
+    """The C3 grid at O(2,6): elf_f<3> forward, the elf_k1 + elf_k2 pair in reverse, 2 shots x 300 steps."""
+    _elastic_vs_oracle(350, 1700, 50, 300, 10.0, 1e-3, 25.0, ns=2, nr=1700, z_sr=10, vti=False, params=("vp", "vs", "rho"),
+                       tag="C3 grid slice, O(2,6) (nt 300, 2 shots)", order=6)
 
 
 def test_c4_slice_vs_oracle():
