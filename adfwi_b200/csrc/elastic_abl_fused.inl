@@ -530,8 +530,10 @@ __device__ __forceinline__ void ab_tile(const CUtensorMap* th, const CUtensorMap
             st4(ltxz + h1, add4(ld4(ltxz + h1), add4(muls(zgath<NN>(wxb, g.c), g.rdz), muls(xgath<NN, 1>(szm, g.c), g.rdx))));
             st4(ltzz + h1, add4(ld4(ltzz + h1), muls(zgath<NN>(wzf, g.c), g.rdz)));
         }
-        __syncthreads();
+        // phase C is an own-cell operation on what THIS thread just stored (tile cell and ring cell alike): no barrier between the
+        // two, except around the free-surface transposes of the top tile row, which mix rows
         if (FS && tzi == 0) {    // 4T: transpose of the free-surface stress edits, on the state cotangents (rows h-2, h-3 end up zero)
+            __syncthreads();
             const int t = tid;
             if (t < RXH) {
                 const int j = X0 + t - HX;
