@@ -355,6 +355,10 @@ def run_reference(args, wl):
                 if tried[th] > 1.1 * min(tried.values()):
                     break
             best = min(tried, key=tried.get)
+            # keep the whole arm within a few minutes whatever the box: shorten the sample (fewer time steps), never the step count
+            total = tried[best] * (max(args.steps, 1) + max(args.warmup, 1))
+            if total > 120.0:
+                nt = max(10, int(nt * 120.0 / total))
             val, sec = reference_gradient_sample(wl, ns, nt, "cpu", reps=max(args.steps, 1), warmup=max(args.warmup, 1), threads=best)
             kind = "reference"
             cores_used = best
