@@ -53,8 +53,33 @@ def elastic(name, abc):
     assert ok
 
 
+def callers():
+    """The 8(f) kernels: fused misfits, a regulariser, the Thomsen -> staggered-moduli chain with its fused padding, GradProcessor."""
+    from adfwi_b200.fwi import misfit as M, regularization as Rg
+    from adfwi_b200.model import thomsen_to_staggered_planes
+    from adfwi_b200.propagator import GradProcessor
+    g = np.load(os.path.join(G, "objective_misfit.npz"))
+    for cls in (M.Misfit_waveform_L2, M.Misfit_global_correlation):
+        sy = torch.tensor(g["syn"], device=dev, requires_grad=True)
+        cls(dt=1.0, normalize=True).forward(torch.tensor(g["obs"], device=dev), sy).backward()
+    rng = np.random.default_rng(0)
+    m = torch.tensor((3000 + 500 * rng.random((60, 90))).astype(np.float32), device=dev, requires_grad=True)
+    for cls in (Rg.TV_1order, Rg.Tikhonov_2order):
+        cls(90, 60, 10.0, 10.0, 1e-3, 1e-3).forward(m).backward()
+    e = np.load(os.path.join(G, "elastic_pml_o4_fs.npz"))
+    par = [torch.tensor(e[k], device=dev, requires_grad=True) for k in ("vp", "vs", "rho", "eps", "delta")]
+    planes = thomsen_to_staggered_planes(*par, anisotropic_type="vti")
+    sum(p.sum() for p in planes).backward()
+    gp = np.load(os.path.join(G, "gradproc_land_full.npz"))
+    GradProcessor(grad_mute=int(gp["kw_grad_mute"]), grad_smooth=int(gp["kw_grad_smooth"]), norm_grad=True, forw_illumination=True,
+                  marine_or_land="land").forward(nx=int(gp["nx"]), nz=int(gp["nz"]), vmax=gp["vmax"][()],
+                                                 grad=torch.tensor(gp["grad"], device=dev), forw=torch.tensor(gp["forw"], device=dev))
+    torch.cuda.synchronize()
+    print("callers: misfits, regularisers, moduli + pad, gradient post-processing ran")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["acoustic", "persist", "pml", "abl"]
+    which = sys.argv[1:] or ["acoustic", "persist", "pml", "abl", "callers"]
     if "acoustic" in which:
         acoustic(False)
     if "persist" in which:
@@ -63,3 +88,5 @@ if __name__ == "__main__":
         elastic("elastic_pml_o4_fs", "PML")
     if "abl" in which:
         elastic("elastic_gerjan_o4_fs", "gerjan")
+    if "callers" in which:
+        callers()
