@@ -126,13 +126,23 @@ __device__ __forceinline__ float4 ldk4(const float* p, uint64_t pol)
 // (tile, shot) sequence of one persistent CTA: items blockIdx.x, +gridDim.x, ...; each item is one
 // tile and one chunk of the group's shots.  The TMA producer runs two shots ahead of the compute
 // along this flat sequence, across tile boundaries.
+// Item order: the adjoint deals the items tile-major (item = tile * nchunks + chunk), the forward kernel chunk-major (item = chunk *
+// ntiles + tile: CTA k and CTA k + 1 then work on neighbouring tiles of the SAME shots).  Measured on the C2 grid: forward 0.0521 ->
+// 0.0505 ms chunk-major, adjoint 0.0587 -> 0.0595 ms (so it keeps tile-major).
+template <bool CM> __device__ __forceinline__ void item_decode(int it, int ntiles, int nchunks, int& tile, int& ch)
+{
+    if (CM) { ch = it / ntiles; tile = it - ch * ntiles; }
+    else    { tile = it / nchunks; ch = it - tile * nchunks; }
+}
+template <bool CM>
 struct Cursor {
     int item, s, s_hi, X0, Z0; bool valid;
     __device__ __forceinline__ void set(int it, const FGeom& g, int s_begin, int s_end, int chunk, int nchunks)
     {
         item = it; valid = it < g.ntx * g.ntz * nchunks;
         if (valid) {
-            const int tile = it / nchunks, ch = it - tile * nchunks;
+            int tile, ch;
+            item_decode<CM>(it, g.ntx * g.ntz, nchunks, tile, ch);
             const int tzi = tile / g.ntx, txi = tile - tzi * g.ntx;
             X0 = txi * TX; Z0 = g.zlo + tzi * TZ;
             s = s_begin + ch * chunk; s_hi = min(s + chunk, s_end);
@@ -143,7 +153,7 @@ struct Cursor {
         if (valid && ++s >= s_hi) set(item + gridDim.x, g, s_begin, s_end, chunk, nchunks);
     }
 };
-__device__ __forceinline__ void issue_stage(const Cursor& c, unsigned char* smem_raw, uint64_t* bar, int k,
+template <bool CM> __device__ __forceinline__ void issue_stage(const Cursor<CM>& c, unsigned char* smem_raw, uint64_t* bar, int k,
                                             const CUtensorMap* t0, const CUtensorMap* t1, const CUtensorMap* t2)
 {
     float* st = (float*)(smem_raw + k * STAGE_BYTES);
@@ -161,7 +171,7 @@ __device__ __forceinline__ void acf_prefetch_3d(const CUtensorMap* tm, int c0, i
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 struct HistMaps { const CUtensorMap *s, *dx, *dz; };
-template <bool G2> __device__ __forceinline__ void adj_prefetch_hist(const Cursor& c, const HistMaps& hm, int hist_len, int tl)
+template <bool G2> __device__ __forceinline__ void adj_prefetch_hist(const Cursor<false>& c, const HistMaps& hm, int hist_len, int tl)
 {
     const int pl = c.s * hist_len + tl;
     acf_prefetch_3d(hm.s, c.X0, c.Z0, pl);
@@ -199,7 +209,7 @@ struct Roles {
 template <bool FS, bool SAVE, bool SAVE2, bool ILLUM, bool PML>
 __device__ __forceinline__ void fwd_tile(const CUtensorMap* tm_p, const CUtensorMap* tm_u, const CUtensorMap* tm_w,
                                          const FGeom& g, const FwdArgs& a, unsigned char* smem_raw, uint64_t* bar,
-                                         uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx, float* s_sv,
+                                         uint32_t& par, int& stage, Cursor<true>& pc, int* s_sz, int* s_sx, float* s_sv,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
 {
     float* pn = (float*)(smem_raw + FWD_STAGES * STAGE_BYTES);
@@ -424,11 +434,12 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
     uint32_t par = 0;
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.nchunks;
-    Cursor pc;
+    Cursor<true> pc;
     pc.set(blockIdx.x, g, a.s_begin, a.s_end, a.chunk, a.nchunks);
     griddep_launch_dependents();
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int tile = item / a.nchunks, chunk = item - tile * a.nchunks;
+        int tile, chunk;
+        item_decode<true>(item, g.ntx * g.ntz, a.nchunks, tile, chunk);
         const int s_lo = a.s_begin + chunk * a.chunk;
         const int s_hi = min(s_lo + a.chunk, a.s_end);
         const bool first = item == (int)blockIdx.x;
@@ -451,7 +462,7 @@ ac_fwd_fused(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ C
 template <bool FS, bool PML, bool G2>
 __device__ __forceinline__ void adj_tile(const CUtensorMap* tm_lp, const CUtensorMap* tm_lu, const CUtensorMap* tm_lw, const HistMaps& hm,
                                          const FGeom& g, const AdjArgs& a, unsigned char* smem_raw, uint64_t* bar,
-                                         uint32_t& par, int& stage, Cursor& pc, int* s_sz, int* s_sx,
+                                         uint32_t& par, int& stage, Cursor<false>& pc, int* s_sz, int* s_sx,
                                          const Roles& R, int tid, int tile, int s_lo, int s_hi, int chunk, bool first)
 {
     float* lp1 = (float*)(smem_raw + ADJ_STAGES * STAGE_BYTES);                  // lambda_p after undoing W,U (and 3T)
@@ -695,7 +706,7 @@ ac_adj_fused(const __grid_constant__ CUtensorMap tm_lp, const __grid_constant__ 
     uint32_t par = 0;
     int stage = 0;
     const int nitems = g.ntx * g.ntz * a.nchunks;
-    Cursor pc;
+    Cursor<false> pc;
     pc.set(blockIdx.x, g, a.s_begin, a.s_end, a.chunk, a.nchunks);
     griddep_launch_dependents();
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
