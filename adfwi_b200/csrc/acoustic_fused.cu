@@ -887,7 +887,8 @@ struct FPlan {
     FGeom g;
     int ns, nr, FS, save, need_g2, n_segments;
     int K, nseg, nckpt, G;
-    int chunk, nchunks;             // shots one CTA walks through per tile; chunks per full group
+    int chunk, nchunks;             // shots one CTA walks through per tile; chunks per full group (forward kernel)
+    int chunk_b, nchunks_b;         // the same for the adjoint kernel
     int cprows; size_t cpplane;
     float* pack;                    // 7 masked coefficient planes
     unsigned char* tflags;
@@ -897,6 +898,37 @@ struct FPlan {
     int *rcv_cnt, *rcv_start, *rcv_cursor, *rcv_id, *rcv_zx; unsigned char* rcv_nbr;
     size_t bytes;
 };
+
+// Shots per (tile, chunk) item of the ADJOINT kernel.  Its items are dealt round-robin, tile-major, to the resident CTAs; with few
+// rounds the deal is simulated for every candidate chunk length c (chunks c, c, ..., remainder) and the cheapest taken: cost = the
+// busiest CTA's shot-steps plus c0 = 0.78 shot-steps per item (fit of tools/c2_chunk_sweep.sh).  C2, 10 shots per launch: 4 + 4 + 2
+// (14 steps for the busiest CTA) instead of 5 + 5 (15): 0.0599 -> 0.0578 ms per launch.  The forward kernel (chunk-major order) is
+// faster with the plain rule below (0.0506 against 0.0516 ms), so it keeps it.
+inline int acf_pick_chunk(int G, int ntiles, int ncta)
+{
+    const float c0 = 0.78f;
+    const int cmax = G < CMAX ? G : CMAX;
+    int best = cmax; float tbest = 3.0e38f;
+    for (int c = cmax; c >= 1; --c) {
+        const int nch = cdiv(G, c);
+        if (c < cmax && cdiv(G, c + 1) == nch) continue;             // same chunk count as the longer candidate, worse remainder
+        const long long nitems = (long long)ntiles * nch;
+        float t;
+        if (nitems > 8LL * ncta) {
+            t = (float)ntiles * ((float)G + c0 * (float)nch) / (float)ncta + (float)c + c0;
+        } else {
+            const int last = G - (nch - 1) * c;
+            t = 0.f;
+            for (int k = 0; k < ncta && k < nitems; ++k) {
+                float load = 0.f;
+                for (long long it = k; it < nitems; it += ncta) load += (float)((int)(it % nch) == nch - 1 ? last : c) + c0;
+                if (load > t) t = load;
+            }
+        }
+        if (t < tbest) { tbest = t; best = c; }
+    }
+    return best;
+}
 
 int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
 {
@@ -930,6 +962,10 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
     int chunk = cdiv(G, nchunks);
     if (chunk > CMAX) chunk = CMAX;
     P->chunk = chunk; P->nchunks = cdiv(G, chunk);
+    int chunk_b = d->reserved[2] > 0 ? d->reserved[2] : d->reserved[1] > 0 ? d->reserved[1] : acf_pick_chunk(G, ntiles, CTAS_PER_SM * nsm);
+    if (chunk_b > G) chunk_b = G;
+    if (chunk_b > CMAX) chunk_b = CMAX;
+    P->chunk_b = chunk_b; P->nchunks_b = cdiv(G, chunk_b);
     Carver cv(ws);
     const size_t sp = (size_t)d->ns * g.plane;
     P->pack = cv.take<float>(7 * P->cpplane);
@@ -943,8 +979,8 @@ int acf_make_plan(const adfwi_acoustic_desc* d, void* ws, FPlan* P, int nsm)
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->lam[b][f] = nullptr;
     if (P->save) {
         for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) P->lam[b][f] = cv.take<float>(sp);
-        P->g1part = cv.take<float>((size_t)P->nchunks * g.plane);
-        if (P->need_g2) P->g2part = cv.take<float>((size_t)P->nchunks * g.plane);
+        P->g1part = cv.take<float>((size_t)P->nchunks_b * g.plane);
+        if (P->need_g2) P->g2part = cv.take<float>((size_t)P->nchunks_b * g.plane);
         if (P->nckpt) P->ckpt = cv.take<float>((size_t)P->nckpt * 3 * sp);
         P->hist = cv.take<float>((size_t)K * sp);
         if (P->need_g2) { P->hist_dx = cv.take<float>((size_t)K * sp); P->hist_dz = cv.take<float>((size_t)K * sp); }
@@ -1042,9 +1078,9 @@ int acf_make_maps(const FPlan& P, StepMaps* M)
     return 0;
 }
 
-inline int acf_grid(const FPlan& P, int nshots, int* nchunks)
+inline int acf_grid(const FPlan& P, int nshots, int* nchunks, bool adjoint = false)
 {
-    *nchunks = cdiv(nshots, P.chunk);
+    *nchunks = cdiv(nshots, adjoint ? P.chunk_b : P.chunk);
     const int nitems = P.g.ntx * P.g.ntz * *nchunks;
     const int cap = CTAS_PER_SM * acf_num_sms();
     return nitems < cap ? nitems : cap;
@@ -1325,8 +1361,8 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
     if (rc) return rc;
     // the coefficient pack, tile flags and receiver buckets were left in the workspace by the forward call
     const int nt = g.nt;
-    ADFWI_CUDA(cudaMemsetAsync(P.g1part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
-    if (P.need_g2) ADFWI_CUDA(cudaMemsetAsync(P.g2part, 0, sizeof(float) * (size_t)P.nchunks * g.plane, st));
+    ADFWI_CUDA(cudaMemsetAsync(P.g1part, 0, sizeof(float) * (size_t)P.nchunks_b * g.plane, st));
+    if (P.need_g2) ADFWI_CUDA(cudaMemsetAsync(P.g2part, 0, sizeof(float) * (size_t)P.nchunks_b * g.plane, st));
     PPlan Q;
     if (pp_make_plan(d, P, &Q)) {
         PAdjArgs a;
@@ -1339,7 +1375,7 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
             else      ADFWI_CUDA(PP_DISPATCH(acp_adj, false, Q.kmax, P.ns, Q.g, Q.smem_adj, st, a));
         }
         ADFWI_LAUNCH_CHECK();
-        acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g1part, g_alpha1);
+        acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks_b, P.g1part, g_alpha1);
         ADFWI_LAUNCH_CHECK();
         return ADFWI_OK;
     }
@@ -1372,8 +1408,8 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
                 a.sx = sx; a.sz = sz; a.hist = P.hist; a.hist_len = P.K; a.tl = it - t0; a.it = it;
                 a.hist_dx = P.hist_dx; a.hist_dz = P.hist_dz;
                 a.nr = P.nr; a.rb = acf_bucket_ptrs(P); a.gp = gp; a.gu = gu; a.gw = gw;
-                a.g1part = P.g1part; a.g2part = P.g2part; a.g_src = g_src; a.s_begin = sb; a.s_end = se; a.chunk = P.chunk;
-                const int grid = acf_grid(P, se - sb, &a.nchunks);
+                a.g1part = P.g1part; a.g2part = P.g2part; a.g_src = g_src; a.s_begin = sb; a.s_end = se; a.chunk = P.chunk_b;
+                const int grid = acf_grid(P, se - sb, &a.nchunks, true);
                 {
                     TimedLaunch tl_(KC_AC_ADJ_FUSED, st);
 #define LA(FSv, G2v) ADFWI_CUDA(acf_launch(ac_adj_fused<FSv, G2v>, grid, ADJ_SMEM, st, acf_use_pdl(), M.lam[lcur][0], M.lam[lcur][1], M.lam[lcur][2], M.hist[0], M.hist[1], M.hist[2], g, a))
@@ -1386,10 +1422,10 @@ int acf_backward(const adfwi_acoustic_desc* d, const float* const* coef, const f
             }
         }
     }
-    acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g1part, g_alpha1);
+    acf_reduce_parts<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks_b, P.g1part, g_alpha1);
     ADFWI_LAUNCH_CHECK();
     if (P.need_g2) {
-        acf_reduce_g2<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks, P.g2part, coef[2], g_alpha2);
+        acf_reduce_g2<<<dim3(cdiv(g.nxp, 128), g.nzp), 128, 0, st>>>(g.nzp, g.nxp, g.ld, g.fs, P.nchunks_b, P.g2part, coef[2], g_alpha2);
         ADFWI_LAUNCH_CHECK();
     }
     return ADFWI_OK;

@@ -107,6 +107,7 @@ class AcousticFD(torch.autograd.Function):
                          0, need[1], config["shots_per_group"])
         desc.reserved[0] = (1 if config["force_generic"] else 0) | (0 if config.get("persistent", True) else 2)
         desc.reserved[1] = int(config.get("shots_per_chunk", 0))
+        desc.reserved[2] = int(config.get("shots_per_chunk_reverse", 0))
         with torch.cuda.device(dev):
             if save:
                 if config["ckpt_interval"] is not None:

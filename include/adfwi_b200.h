@@ -63,7 +63,7 @@ typedef struct {
     int32_t shots_per_group; /* shots advanced per kernel launch; 0 = library picks (all) */
     int32_t reserved[4];     /* [0] bit 0: force the generic (unfused) kernels, bit 1: never use the cluster-persistent
                                 small-grid kernels; [1]: shots one CTA of the fused kernels walks through per tile
-                                (0 = library picks); rest 0 */
+                                (0 = library picks); [2]: the same for the adjoint kernel only; rest 0 */
 } adfwi_acoustic_desc;
 
 /* bytes of workspace forward(+backward) needs for this descriptor (0 on invalid desc) */
