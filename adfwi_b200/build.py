@@ -19,6 +19,7 @@ SOURCES = ["api.cu", "acoustic.cu", "acoustic_fused.cu", "elastic.cu", "elastic_
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC,-O2", "-shared", "-ldl",
+    "--threads", "0",          # the eight translation units compile in parallel (elastic_fused.cu alone takes most of the time)
 ]
 
 
